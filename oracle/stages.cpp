@@ -1,0 +1,305 @@
+// TEST INFRASTRUCTURE ONLY (see tile.hpp header).
+//
+// Scalar restatements of the reference's own CUDA kernels after the SGM stage:
+//   interpolateKernel                 /root/reference/src/modules/disparity/interpolation.cu:17-82
+//   calculateDirectionalDerivatives   /root/reference/src/modules/disparity/derivative.cu:27-97
+//   mergeDerivativeHistograms         /root/reference/src/modules/disparity/derivative.cu:99-116
+//   calculateDerivatives (naive)      /root/reference/src/modules/planeseg/planeseg.cu:31-142
+//   classifyPlanes (naive)            /root/reference/src/modules/planeseg/planeseg.cu:160-243 (no temporal vote)
+//   performSuperPixelClassifications  /root/reference/src/modules/planeseg/sp_planeseg.cu:25-134 (no temporal vote)
+//   classifyPlanes (SP)               /root/reference/src/modules/planeseg/sp_planeseg.cu:136-184
+//   HistogramPeak parameter update    /root/reference/src/modules/planeseg/planeseg.cu:405-458
+//   util::findPeaks                   /root/reference/src/utils/peaks.cpp:12-72
+// Tile semantics come from tile.hpp (copyToShared, bug-compatible).  Canonical choices where the
+// reference races: Q10 low-pass is out-of-place, Q11 interpolation is Jacobi,
+// Q17 histograms are recounted from the oracle's own derivative image.
+// Pinned against the real reference kernels (built by oracle/ref/, run on a B200) through the golden
+// vectors in tests/golden/ on the "defined" masks this file produces.
+#include <algorithm>
+#include <climits>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "oracle.h"
+#include "tile.hpp"
+
+using orc::ceil_div;
+using orc::Tile;
+
+static const int16_t INVALID = -32768;  // CARTSLAM_DISPARITY_INVALID, disparity.hpp:17
+
+extern "C" {
+
+// interpolation.cu:17-82, launch :85-99 (16x16 threads, 4x4 batch -> 64x64 tile, dynamic smem exactly sized).
+// disp is updated in place; `defined` (may be null) gets 1 where the reference's result does not
+// depend on uninitialised / out-of-image memory.
+int orc_interpolate(int16_t* disp, int W, int H, int radius, int iterations, int minDisparity, int maxDisparity,
+                    uint8_t* defined) {
+    if (radius <= 0) return 0;
+    const int BD = 16, XB = 4, YB = 4, TW = BD * XB, TH = BD * YB, pad = radius - 1;
+    const size_t alloc = (size_t)(TW + 2 * pad) * (TH + 2 * pad);  // SHARED_SIZE(radius), :13
+    const unsigned minCount = (unsigned)(radius * radius + 1);     // :33
+    std::vector<int16_t> out(disp, disp + (size_t)W * H);
+    Tile<int16_t> t;
+    for (int by = 0; by < ceil_div(H, TH); ++by)
+        for (int bx = 0; bx < ceil_div(W, TW); ++bx) {
+            orc::copy_to_shared<int16_t, true>(t, disp, W, H, bx, by, BD, BD, XB, YB, pad, pad, alloc, INVALID);
+            for (int it = 0; it < iterations; ++it) {
+                // Q11 canonical schedule: Jacobi (all reads see the previous iteration)
+                std::vector<int16_t> ns = t.s;
+                std::vector<uint8_t> nd = t.def;
+                for (int ly = 0; ly < TH; ++ly)
+                    for (int lx = 0; lx < TW; ++lx) {
+                        if (bx * TW + lx >= W || by * TH + ly >= H) continue;
+                        int sum = 0, count = 0;
+                        bool d = true;
+                        for (int k = -radius + 1; k < radius; ++k)
+                            for (int l = -radius + 1; l < radius; ++l) {
+                                bool dd;
+                                const int16_t v = t.get(lx + k, ly + l, &dd);
+                                d = d && dd;
+                                if (v > minDisparity && v < maxDisparity) {  // :52 (upper bound is NOT x16, Q11)
+                                    sum += v;
+                                    count++;
+                                }
+                            }
+                        const long idx = t.index(lx, ly);
+                        ns[idx] = ((unsigned)count > minCount) ? (int16_t)(sum / count) : INVALID;
+                        nd[idx] = d;
+                    }
+                t.s.swap(ns);
+                t.def.swap(nd);
+            }
+            for (int ly = 0; ly < TH; ++ly)
+                for (int lx = 0; lx < TW; ++lx) {
+                    const int x = bx * TW + lx, y = by * TH + ly;
+                    if (x >= W || y >= H) continue;
+                    bool d;
+                    out[(size_t)y * W + x] = t.get(lx, ly, &d);
+                    if (defined) defined[(size_t)y * W + x] = d;
+                }
+        }
+    std::memcpy(disp, out.data(), sizeof(int16_t) * (size_t)W * H);
+    return 0;
+}
+
+// derivative.cu:27-116. deriv: [H][W][2] (ch0 vertical, ch1 horizontal); hist: [256][2] int32;
+// defined: [H][W][2] or null.
+int orc_derivative(const int16_t* disp, int W, int H, int16_t* deriv, int32_t* hist, uint8_t* defined) {
+    const int BD = 32, XB = 4, YB = 4, TW = 128, TH = 128, OFF = 2;
+    const size_t alloc = (size_t)(OFF * 2 + TW) * (OFF * 2 + TH);  // SHARED_SIZE, :23
+    std::memset(hist, 0, sizeof(int32_t) * 512);
+    Tile<int16_t> t;
+    for (int by = 0; by < ceil_div(H, TH); ++by)
+        for (int bx = 0; bx < ceil_div(W, TW); ++bx) {
+            orc::copy_to_shared<int16_t, true>(t, disp, W, H, bx, by, BD, BD, XB, YB, OFF, OFF, alloc, INVALID);
+            for (int ly = 0; ly < TH; ++ly)
+                for (int lx = 0; lx < TW; ++lx) {
+                    const int x = bx * TW + lx, y = by * TH + ly;
+                    if (x >= W || y >= H) continue;
+                    bool du, dd, dl, dr;
+                    const int16_t up = t.get(lx, ly - OFF, &du), dn = t.get(lx, ly + OFF, &dd);
+                    const int16_t lf = t.get(lx - OFF, ly, &dl), rt = t.get(lx + OFF, ly, &dr);
+                    const int16_t dv = (int16_t)(dn - up), dh = (int16_t)(rt - lf);
+                    const bool vv = up != INVALID && dn != INVALID, hv = lf != INVALID && rt != INVALID;
+                    const int16_t ov = vv ? dv : INVALID, oh = hv ? dh : INVALID;
+                    const size_t o = ((size_t)y * W + x) * 2;
+                    deriv[o] = ov;
+                    deriv[o + 1] = oh;
+                    if (defined) {
+                        defined[o] = du && dd;
+                        defined[o + 1] = dl && dr;
+                    }
+                    // Q17: histogram recounted from the oracle's own output
+                    if (vv && dv >= -128 && dv <= 127) hist[2 * (dv + 128)]++;
+                    if (hv && dh >= -128 && dh <= 127) hist[2 * (dh + 128) + 1]++;
+                }
+        }
+    return 0;
+}
+
+// planeseg.cu:31-142 (calculateDerivatives). deriv: [H][W] s16; hist: this frame's 256-bin histogram
+// (the reference adds it to a running total, planeseg.cu:144-158 - kept by the caller); defined or null.
+int orc_naive_derivative(const int16_t* disp, int W, int H, int16_t* deriv, int32_t* hist, uint8_t* defined) {
+    const int BD = 32, XB = 4, YB = 4, TW = 128, TH = 128, PADY = 2;
+    const size_t alloc = (size_t)(XB * BD) * (YB * (PADY * 2 + BD));  // SHARED_SIZE, planeseg.cu:20 (over-allocated)
+    std::memset(hist, 0, sizeof(int32_t) * 256);
+    Tile<int16_t> t;
+    for (int by = 0; by < ceil_div(H, TH); ++by)
+        for (int bx = 0; bx < ceil_div(W, TW); ++bx) {
+            orc::copy_to_shared<int16_t, true>(t, disp, W, H, bx, by, BD, BD, XB, YB, PADY, 0, alloc, INVALID);  // Q9
+            // vertical 5-tap valid-mean over local rows 0..TH-1, all TW columns (no bounds test, :60-104).
+            // Q10 canonical schedule: out-of-place (every tap reads the unfiltered tile).
+            std::vector<int16_t> F((size_t)TW * TH);
+            std::vector<uint8_t> Fd((size_t)TW * TH);
+            for (int ly = 0; ly < TH; ++ly)
+                for (int lx = 0; lx < TW; ++lx) {
+                    int16_t sum = 0;  // derivative_t sum, :62 (16-bit accumulate)
+                    int count = 0;
+                    bool d = true;
+                    for (int k = -PADY; k <= PADY; ++k) {
+                        bool dd;
+                        const int16_t v = t.get(lx, ly + k, &dd);
+                        d = d && dd;
+                        if (v != INVALID) {
+                            sum = (int16_t)(sum + v);
+                            count++;
+                        }
+                    }
+                    F[(size_t)ly * TW + lx] = count == 0 ? INVALID : (int16_t)(sum / count);
+                    Fd[(size_t)ly * TW + lx] = d;
+                }
+            auto Fget = [&](int lx, int ly, bool& d) -> int16_t {
+                if (ly >= 0 && ly < TH) {  // filtered rows
+                    d = Fd[(size_t)ly * TW + lx] != 0;
+                    return F[(size_t)ly * TW + lx];
+                }
+                bool dd;  // Q10b: halo rows stay unfiltered
+                const int16_t v = t.get(lx, ly, &dd);
+                d = dd;
+                return v;
+            };
+            for (int ly = 0; ly < TH; ++ly)
+                for (int lx = 0; lx < TW; ++lx) {
+                    const int x = bx * TW + lx, y = by * TH + ly;
+                    if (x >= W || y >= H) continue;
+                    bool d0, d1, d2;
+                    const int16_t c = Fget(lx, ly, d0), n = Fget(lx, ly + 1, d1), p = Fget(lx, ly - 1, d2);
+                    const int16_t dv = (int16_t)(n - p);
+                    const bool valid = c != INVALID && n != INVALID && p != INVALID;
+                    deriv[(size_t)y * W + x] = valid ? dv : INVALID;
+                    if (defined) defined[(size_t)y * W + x] = d0 && d1 && d2;
+                    if (valid && dv >= -128 && dv <= 127) hist[dv + 128]++;
+                }
+        }
+    return 0;
+}
+
+// planeseg.cu:188-197 / sp_planeseg.cu:68-77: range rule on one derivative channel.
+// deriv has `stride` int16 per pixel (1 naive, 2 for CV_16SC2 ch0). params = {hS,hE,vS,vE}.
+int orc_classify(const int16_t* deriv, long n, int stride, int hS, int hE, int vS, int vE, uint8_t* planes) {
+    for (long i = 0; i < n; ++i) {
+        const int16_t d = deriv[i * stride];
+        uint8_t p = 2;  // UNKNOWN
+        if (d != INVALID && d >= hS && d < hE)
+            p = 0;  // HORIZONTAL
+        else if (d != INVALID && d >= vS && d < vE)
+            p = 1;  // VERTICAL
+        planes[i] = p;
+    }
+    return 0;
+}
+
+// sp_planeseg.cu:25-184 with previousPlanesCount == 0.
+// labels u16 [H][W]; maxLabel = label COUNT (a11).  Returns -2 if a label >= maxLabel occurs,
+// -3 when (maxLabel+1)*6 > 32768 (sp_planeseg.cu:327-331), -4 if a vote counter would exceed u16.
+int orc_sp_planeseg(const int16_t* deriv2, const uint16_t* labels, int W, int H, int maxLabel, int hS, int hE, int vS,
+                    int vE, uint8_t* planesUnsmoothed, uint8_t* planes) {
+    if ((size_t)(maxLabel + 1) * 3 * sizeof(uint16_t) > 32768) return -3;
+    const long N = (long)W * H;
+    orc_classify(deriv2, N, 2, hS, hE, vS, vE, planesUnsmoothed);
+    std::vector<uint32_t> votes((size_t)maxLabel * 3, 0);
+    for (long i = 0; i < N; ++i) {
+        if (labels[i] >= maxLabel) return -2;
+        if (++votes[(size_t)labels[i] * 3 + planesUnsmoothed[i]] > 65535u) return -4;
+    }
+    std::vector<uint8_t> assign(maxLabel);
+    for (int l = 0; l < maxLabel; ++l) {
+        int maxVotes = (int)votes[(size_t)l * 3 + 2];
+        uint8_t best = 2;
+        const int v = (int)votes[(size_t)l * 3 + 1], h = (int)votes[(size_t)l * 3 + 0];
+        if (v > maxVotes) {
+            maxVotes = v;
+            best = 1;
+        }
+        if (h > maxVotes) best = 0;
+        assign[l] = best;
+    }
+    for (long i = 0; i < N; ++i) planes[i] = assign[labels[i]];
+    return 0;
+}
+
+// ---- host-side parameter estimation --------------------------------------------------------------
+
+struct Peak {
+    int born, left, right, died;
+    int persistence(const int32_t* h) const { return died == -1 ? INT_MAX : h[born] - h[died]; }
+};
+
+// peaks.cpp:12-72 (same std::sort calls, same comparators)
+static std::vector<Peak> find_peaks(const int32_t* data, int n) {
+    std::vector<Peak> peaks;
+    std::vector<int> idxtopeak(n, -1), indices(n);
+    for (int i = 0; i < n; ++i) indices[i] = i;
+    std::sort(indices.begin(), indices.end(), [&](int a, int b) { return data[a] > data[b]; });
+    for (int idx : indices) {
+        const bool lftdone = idx > 0 && idxtopeak[idx - 1] != -1;
+        const bool rgtdone = idx < n - 1 && idxtopeak[idx + 1] != -1;
+        const int il = lftdone ? idxtopeak[idx - 1] : -1;
+        const int ir = rgtdone ? idxtopeak[idx + 1] : -1;
+        if (!lftdone && !rgtdone) {
+            peaks.push_back(Peak{idx, idx, idx, -1});
+            idxtopeak[idx] = (int)peaks.size() - 1;
+        } else if (lftdone && !rgtdone) {
+            peaks[il].right += 1;
+            idxtopeak[idx] = il;
+        } else if (!lftdone && rgtdone) {
+            peaks[ir].left -= 1;
+            idxtopeak[idx] = ir;
+        } else {
+            if (data[peaks[il].born] > data[peaks[ir].born]) {
+                peaks[ir].died = idx;
+                peaks[il].right = peaks[ir].right;
+                idxtopeak[peaks[il].right] = idxtopeak[idx] = il;
+            } else {
+                peaks[il].died = idx;
+                peaks[ir].left = peaks[il].left;
+                idxtopeak[peaks[ir].left] = idxtopeak[idx] = ir;
+            }
+        }
+    }
+    std::sort(peaks.begin(), peaks.end(), [&](Peak a, Peak b) { return a.persistence(data) > b.persistence(data); });
+    return peaks;
+}
+
+// out: up to maxPeaks rows of {born,left,right,died}; returns the number of peaks found.
+int orc_find_peaks(const int32_t* hist, int n, int* out, int maxPeaks) {
+    auto p = find_peaks(hist, n);
+    for (int i = 0; i < (int)p.size() && i < maxPeaks; ++i) {
+        out[4 * i] = p[i].born;
+        out[4 * i + 1] = p[i].left;
+        out[4 * i + 2] = p[i].right;
+        out[4 * i + 3] = p[i].died;
+    }
+    return (int)p.size();
+}
+
+// planeseg.cu:405-458. params = {horizontalCenter, verticalCenter, hS, hE, vS, vE}, updated in place.
+// Returns 1 if the ranges were updated, 0 if one of the early returns fired (ranges untouched; the
+// centres are assigned before those returns, as in the reference).
+int orc_histogram_peak_update(const int32_t* hist, int* params) {
+    auto peaks = find_peaks(hist, 256);
+    if (peaks.size() < 2) return 0;
+    if (std::abs(peaks[0].born - 128) > std::abs(peaks[1].born - 128)) std::swap(peaks[0], peaks[1]);
+    // NOTE: the reference assigns the centres before the early returns below (planeseg.cu:418-419)
+    params[1] = peaks[0].born - 128;
+    params[0] = peaks[1].born - 128;
+    int minIndex = std::min(peaks[0].born, peaks[1].born);
+    for (int i = minIndex; i < std::max(peaks[0].born, peaks[1].born); ++i)
+        if (hist[i] < hist[minIndex]) minIndex = i;
+    const int vDist = std::abs(minIndex - peaks[0].born), hDist = std::abs(minIndex - peaks[1].born);
+    if (vDist == 0 || hDist == 0) return 0;
+    const int vDer = (hist[peaks[0].born] - hist[minIndex]) / vDist;
+    const int hDer = (hist[peaks[1].born] - hist[minIndex]) / hDist;
+    if (vDer == 0 || hDer == 0) return 0;
+    const int vWidth = hist[peaks[0].born] / vDer, hWidth = hist[peaks[1].born] / hDer;
+    params[4] = peaks[0].born - vWidth - 128;
+    params[5] = minIndex - 127;
+    params[2] = minIndex - 127;
+    params[3] = peaks[1].born + hWidth - 127;
+    return 1;
+}
+
+}  // extern "C"
