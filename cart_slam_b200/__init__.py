@@ -1,0 +1,446 @@
+"""cart_slam_b200 - Python binding (ctypes) of libcartb200, the B200-native disparity -> planeseg path.
+
+PyTorch is used for device memory and streams only; every computation happens in the hand-written
+sm_100a kernels behind the C ABI declared in include/cartb200.h.  There is no CPU fallback: importing
+this package without the compiled library, or creating a Context without a GPU, fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libcartb200.so")
+
+OK, E_ARG, E_SHAPE, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+DISPARITY_INVALID = -32768
+PLANE_HORIZONTAL, PLANE_VERTICAL, PLANE_UNKNOWN = 0, 1, 2
+
+# data keys of the reference's module hand-off
+KEY_DISPARITY = "disparity"
+KEY_DISPARITY_DERIVATIVE = "disparity_derivative"
+KEY_DISPARITY_DERIVATIVE_HISTOGRAM = "disparity_derivative_histogram"
+KEY_SUPERPIXELS = "superpixels"
+KEY_SUPERPIXELS_MAX_LABEL = "superpixels_max_label"
+KEY_PLANES = "planes"
+KEY_PLANES_UNSMOOTHED = "planes_unsmoothed"
+
+
+class CartB200Error(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"cartb200 error {code}: {message}")
+        self.code = code
+
+
+class _CConfig(C.Structure):
+    _fields_ = [
+        ("width", C.c_int), ("height", C.c_int), ("max_batch", C.c_int),
+        ("min_disparity", C.c_int), ("num_disparities", C.c_int), ("p1", C.c_int), ("p2", C.c_int),
+        ("uniqueness_ratio", C.c_int), ("paths", C.c_int), ("smoothing_radius", C.c_int),
+        ("smoothing_iterations", C.c_int), ("enable_superpixels", C.c_int), ("sp_block_size", C.c_int),
+        ("sp_direct_clique_cost", C.c_double), ("sp_diagonal_clique_cost", C.c_double),
+        ("sp_compactness_weight", C.c_double), ("sp_progressive_compactness_cost", C.c_double),
+        ("sp_image_weight", C.c_double), ("sp_disparity_weight", C.c_double),
+    ]
+
+
+class _CSeqOpts(C.Structure):
+    _fields_ = [
+        ("pipeline", C.c_int), ("provider", C.c_int), ("static_params", C.c_int * 4),
+        ("update_interval", C.c_int), ("reset_interval", C.c_int), ("sp_initial_iterations", C.c_int),
+        ("sp_iterations", C.c_int), ("sp_reset_iterations", C.c_int), ("start_id", C.c_int),
+    ]
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+            "cart_slam_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(_LIB_PATH)
+    lib.cartb200_version.restype = C.c_char_p
+    lib.cartb200_last_error.restype = C.c_char_p
+    lib.cartb200_last_error.argtypes = [C.c_void_p]
+    lib.cartb200_launch_count.restype = C.c_longlong
+    lib.cartb200_launch_count.argtypes = [C.c_void_p]
+    lib.cartb200_scratch_bytes.restype = C.c_size_t
+    lib.cartb200_scratch_bytes.argtypes = [C.c_void_p]
+    lib.cartb200_create.argtypes = [C.POINTER(_CConfig), C.POINTER(C.c_void_p)]
+    lib.cartb200_destroy.argtypes = [C.c_void_p]
+    lib.cartb200_default_config.argtypes = [C.POINTER(_CConfig), C.c_int, C.c_int]
+    lib.cartb200_default_sequence_opts.argtypes = [C.POINTER(_CSeqOpts)]
+    vp, sz, i = C.c_void_p, C.c_size_t, C.c_int
+    lib.cartb200_disparity.argtypes = [vp, i, vp, vp, sz, sz, vp, sz, sz, vp]
+    lib.cartb200_sgm_gray_census.argtypes = [vp, i, vp, vp, sz, sz, vp]
+    lib.cartb200_sgm_aggregate.argtypes = [vp, i, vp]
+    lib.cartb200_sgm_wta_post.argtypes = [vp, i, vp, sz, sz, vp]
+    lib.cartb200_interpolate.argtypes = [vp, i, vp, sz, sz, i, i, i, i, vp]
+    lib.cartb200_sgm_intermediate.argtypes = [vp, i, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
+    lib.cartb200_derivative.argtypes = [vp, i, vp, sz, sz, vp, sz, sz, vp, vp]
+    lib.cartb200_naive_derivative.argtypes = [vp, i, vp, sz, sz, vp, sz, sz, vp, vp]
+    lib.cartb200_classify.argtypes = [vp, i, vp, sz, sz, i, i, vp, vp, sz, sz, vp]
+    lib.cartb200_superpixels_reset.argtypes = [vp, i, vp, C.POINTER(i), vp]
+    lib.cartb200_superpixels_relax.argtypes = [vp, i, vp, i, vp, sz, sz, vp, sz, sz, vp, sz, sz, vp]
+    lib.cartb200_superpixels_set_labels.argtypes = [vp, i, vp, sz, vp]
+    lib.cartb200_superpixels_border_map.argtypes = [vp, vp, sz, vp, sz, vp]
+    lib.cartb200_sp_planeseg.argtypes = [vp, i, vp, sz, sz, vp, sz, sz, i, vp, vp, vp, sz, sz, vp]
+    lib.cartb200_histogram_peak_update.argtypes = [vp, vp]
+    lib.cartb200_run_sequence_host.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp, vp]
+    lib.cartb200_run_sequence_device.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp, vp, vp]
+    lib.cartb200_debug_ref_tile_i32.restype = C.c_int32
+    lib.cartb200_debug_ref_tile_i32.argtypes = [vp] + [i] * 11 + [C.c_long, C.c_int32, i, i]
+    lib.cartb200_debug_median9.restype = C.c_uint32
+    lib.cartb200_debug_median9.argtypes = [vp]
+    return lib
+
+
+_lib = _load()
+
+EXPORTED_SYMBOLS = [
+    "cartb200_default_config", "cartb200_create", "cartb200_destroy", "cartb200_last_error", "cartb200_version",
+    "cartb200_launch_count", "cartb200_scratch_bytes", "cartb200_disparity", "cartb200_sgm_gray_census",
+    "cartb200_sgm_aggregate", "cartb200_sgm_wta_post", "cartb200_interpolate", "cartb200_sgm_intermediate",
+    "cartb200_derivative", "cartb200_naive_derivative", "cartb200_classify", "cartb200_superpixels_reset",
+    "cartb200_superpixels_relax", "cartb200_superpixels_set_labels", "cartb200_superpixels_border_map",
+    "cartb200_sp_planeseg", "cartb200_histogram_peak_update", "cartb200_default_sequence_opts",
+    "cartb200_run_sequence_host", "cartb200_run_sequence_device", "cartb200_debug_ref_tile_i32",
+]
+
+
+def version() -> str:
+    return _lib.cartb200_version().decode()
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+@dataclass
+class Config:
+    """Mirror of cartb200_config; defaults = the reference's JSON defaults (cartconfig.cpp:121-152)."""
+    width: int
+    height: int
+    max_batch: int = 1
+    min_disparity: int = 4
+    num_disparities: int = 256
+    p1: int = 10
+    p2: int = 120
+    uniqueness_ratio: int = 12
+    paths: int = 4
+    smoothing_radius: int = -1
+    smoothing_iterations: int = 5
+    enable_superpixels: bool = True
+    sp_block_size: int = 12
+    sp_direct_clique_cost: float = 0.5
+    sp_diagonal_clique_cost: Optional[float] = None
+    sp_compactness_weight: float = 0.1
+    sp_progressive_compactness_cost: float = 0.0
+    sp_image_weight: float = 1.5
+    sp_disparity_weight: float = 1.0
+
+    def to_c(self) -> _CConfig:
+        c = _CConfig()
+        _lib.cartb200_default_config(C.byref(c), self.width, self.height)
+        for name, _ in _CConfig._fields_:
+            v = getattr(self, name)
+            if name == "sp_diagonal_clique_cost" and v is None:
+                v = self.sp_direct_clique_cost / np.sqrt(2.0)
+            setattr(c, name, int(v) if isinstance(getattr(c, name), int) else float(v))
+        return c
+
+
+@dataclass
+class SequenceOptions:
+    pipeline: int = 0            # 0 naive (kitti-naive-segmentation.json), 1 superpixel (kitti-planeseg.json)
+    provider: int = 1            # 0 static, 1 histogram_peak
+    static_params: Sequence[int] = field(default_factory=lambda: [1, 30, -3, 1])
+    update_interval: int = 30
+    reset_interval: int = 10
+    sp_initial_iterations: int = 18
+    sp_iterations: int = 6
+    sp_reset_iterations: int = 64
+    start_id: int = 1
+
+    def to_c(self) -> _CSeqOpts:
+        o = _CSeqOpts()
+        _lib.cartb200_default_sequence_opts(C.byref(o))
+        o.pipeline, o.provider = self.pipeline, self.provider
+        for k in range(4):
+            o.static_params[k] = int(self.static_params[k])
+        o.update_interval, o.reset_interval = self.update_interval, self.reset_interval
+        o.sp_initial_iterations, o.sp_iterations = self.sp_initial_iterations, self.sp_iterations
+        o.sp_reset_iterations, o.start_id = self.sp_reset_iterations, self.start_id
+        return o
+
+
+def histogram_peak_update(hist256, params):
+    """HistogramPeakPlaneParameterProvider::updatePlaneParameters. params = [hC, vC, hS, hE, vS, vE]."""
+    h = np.ascontiguousarray(hist256, dtype=np.int32)
+    p = np.array(params, dtype=np.int32)
+    assert h.size == 256 and p.size == 6
+    r = _lib.cartb200_histogram_peak_update(h.ctypes.data, p.ctypes.data)
+    if r < 0:
+        raise CartB200Error(r, "histogram_peak_update")
+    return bool(r), [int(v) for v in p]
+
+
+def debug_ref_tile_i32(img, bx, by, bdx, bdy, XB, YB, y_pad, x_pad, interp, lx, ly, alloc_elems=None, undef=-1):
+    img = np.ascontiguousarray(img, dtype=np.int32)
+    H, W = img.shape
+    if alloc_elems is None:
+        alloc_elems = (XB * bdx + 2 * x_pad) * (YB * bdy + 2 * y_pad)
+    return int(_lib.cartb200_debug_ref_tile_i32(img.ctypes.data, W, H, bx, by, bdx, bdy, XB, YB, y_pad, x_pad,
+                                                int(interp), alloc_elems, undef, lx, ly))
+
+
+def debug_median9(v9) -> int:
+    v = np.ascontiguousarray(v9, dtype=np.uint16)
+    assert v.size == 9
+    return int(_lib.cartb200_debug_median9(v.ctypes.data))
+
+
+class _DevView:
+    def __init__(self, ptr, shape, typestr, strides):
+        self.__cuda_array_interface__ = {"data": (ptr, False), "shape": shape, "typestr": typestr,
+                                         "strides": strides, "version": 2}
+
+
+class Context:
+    """One cartb200 context (scratch sized for `max_batch` frames). Not thread-safe."""
+
+    def __init__(self, cfg: Config):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise CartB200Error(E_CUDA, "no CUDA device: the cartb200 path has no CPU fallback")
+        self.torch = torch
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        c = cfg.to_c()
+        rc = _lib.cartb200_create(C.byref(c), C.byref(self._h))
+        if rc != OK:
+            raise CartB200Error(rc, "cartb200_create failed (see stderr)")
+        self.W, self.H, self.D, self.B = cfg.width, cfg.height, cfg.num_disparities, cfg.max_batch
+        self.max_label = -(-cfg.width // cfg.sp_block_size) * -(-cfg.height // cfg.sp_block_size)
+
+    def close(self):
+        if self._h:
+            _lib.cartb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != OK:
+            raise CartB200Error(rc, _lib.cartb200_last_error(self._h).decode())
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def _img(self, t, dtype, last=None):
+        torch = self.torch
+        assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), (t.dtype, t.is_cuda, t.is_contiguous())
+        assert t.shape[1] == self.H and t.shape[2] == self.W, t.shape
+        if last is not None:
+            assert t.dim() == 4 and t.shape[3] == last
+        n = t.shape[0]
+        pitch = t.stride(1) * t.element_size()
+        fstride = t.stride(0) * t.element_size()
+        return n, C.c_void_p(t.data_ptr()), pitch, fstride
+
+    def launch_count(self) -> int:
+        return int(_lib.cartb200_launch_count(self._h))
+
+    def scratch_bytes(self) -> int:
+        return int(_lib.cartb200_scratch_bytes(self._h))
+
+    # -- disparity -------------------------------------------------------------------------------
+    def disparity(self, left, right):
+        torch = self.torch
+        n, lp, pitch, fs = self._img(left, torch.uint8, 3)
+        n2, rp, pitch2, fs2 = self._img(right, torch.uint8, 3)
+        assert (n, pitch, fs) == (n2, pitch2, fs2)
+        out = torch.empty((n, self.H, self.W), dtype=torch.int16, device=left.device)
+        self._check(_lib.cartb200_disparity(self._h, n, lp, rp, pitch, fs, out.data_ptr(), self.W * 2,
+                                            self.W * self.H * 2, self._stream()))
+        return out
+
+    def sgm_gray_census(self, left, right):
+        torch = self.torch
+        n, lp, pitch, fs = self._img(left, torch.uint8, 3)
+        _, rp, _, _ = self._img(right, torch.uint8, 3)
+        self._check(_lib.cartb200_sgm_gray_census(self._h, n, lp, rp, pitch, fs, self._stream()))
+        return n
+
+    def sgm_aggregate(self, n):
+        self._check(_lib.cartb200_sgm_aggregate(self._h, n, self._stream()))
+
+    def sgm_wta_post(self, n):
+        torch = self.torch
+        out = torch.empty((n, self.H, self.W), dtype=torch.int16, device="cuda")
+        self._check(_lib.cartb200_sgm_wta_post(self._h, n, out.data_ptr(), self.W * 2, self.W * self.H * 2, self._stream()))
+        return out
+
+    def sgm_intermediate(self, which: int, n: int):
+        """Copy of an intermediate of the last SGM call as a torch tensor [n, H, W(, D)]."""
+        torch = self.torch
+        ptr, pitch, fs = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._check(_lib.cartb200_sgm_intermediate(self._h, which, C.byref(ptr), C.byref(pitch), C.byref(fs)))
+        if which >= 10:
+            v = _DevView(ptr.value, (n, self.H, self.W, self.D), "|u1", (fs.value, pitch.value, self.D, 1))
+        else:
+            ts, es = {0: ("<u4", 4), 1: ("<u4", 4), 2: ("|u1", 1), 3: ("<u2", 2), 4: ("<u2", 2)}[which]
+            v = _DevView(ptr.value, (n, self.H, self.W), ts, (fs.value, pitch.value, es))
+        t = torch.as_tensor(v, device="cuda")
+        return t.clone()
+
+    def interpolate(self, disp, radius, iterations, min_disparity, max_disparity):
+        torch = self.torch
+        n, p, pitch, fs = self._img(disp, torch.int16)
+        self._check(_lib.cartb200_interpolate(self._h, n, p, pitch, fs, radius, iterations, min_disparity,
+                                              max_disparity, self._stream()))
+        return disp
+
+    # -- derivative / planeseg -------------------------------------------------------------------
+    def derivative(self, disp):
+        torch = self.torch
+        n, p, pitch, fs = self._img(disp, torch.int16)
+        deriv = torch.empty((n, self.H, self.W, 2), dtype=torch.int16, device=disp.device)
+        hist = torch.empty((n, 256, 2), dtype=torch.int32, device=disp.device)
+        self._check(_lib.cartb200_derivative(self._h, n, p, pitch, fs, deriv.data_ptr(), self.W * 4,
+                                             self.W * self.H * 4, hist.data_ptr(), self._stream()))
+        return deriv, hist
+
+    def naive_derivative(self, disp):
+        torch = self.torch
+        n, p, pitch, fs = self._img(disp, torch.int16)
+        deriv = torch.empty((n, self.H, self.W), dtype=torch.int16, device=disp.device)
+        hist = torch.empty((n, 256), dtype=torch.int32, device=disp.device)
+        self._check(_lib.cartb200_naive_derivative(self._h, n, p, pitch, fs, deriv.data_ptr(), self.W * 2,
+                                                   self.W * self.H * 2, hist.data_ptr(), self._stream()))
+        return deriv, hist
+
+    def _params(self, params, n):
+        p = np.ascontiguousarray(params, dtype=np.int32).reshape(-1, 4)
+        if p.shape[0] == 1 and n > 1:
+            p = np.repeat(p, n, axis=0)
+        assert p.shape[0] == n
+        return np.ascontiguousarray(p)
+
+    def classify(self, deriv, params):
+        """deriv: [n,H,W] (naive) or [n,H,W,2] (channel 0 is used). params: [n][hS,hE,vS,vE]."""
+        torch = self.torch
+        channels = 1 if deriv.dim() == 3 else deriv.shape[3]
+        n, p, pitch, fs = self._img(deriv, torch.int16)
+        pr = self._params(params, n)
+        planes = torch.empty((n, self.H, self.W), dtype=torch.uint8, device=deriv.device)
+        self._check(_lib.cartb200_classify(self._h, n, p, pitch, fs, channels, 0, pr.ctypes.data, planes.data_ptr(),
+                                           self.W, self.W * self.H, self._stream()))
+        torch.cuda.current_stream().synchronize()  # params were read from pageable host memory
+        return planes
+
+    def sp_planeseg(self, deriv, labels, params, max_label=None):
+        torch = self.torch
+        n, dp, dpitch, dfs = self._img(deriv, torch.int16, 2)
+        n2, lp, lpitch, lfs = self._img(labels, torch.uint16)
+        assert n == n2
+        pr = self._params(params, n)
+        unsm = torch.empty((n, self.H, self.W), dtype=torch.uint8, device=deriv.device)
+        planes = torch.empty_like(unsm)
+        self._check(_lib.cartb200_sp_planeseg(self._h, n, dp, dpitch, dfs, lp, lpitch, lfs,
+                                              self.max_label if max_label is None else max_label, pr.ctypes.data,
+                                              unsm.data_ptr(), planes.data_ptr(), self.W, self.W * self.H, self._stream()))
+        torch.cuda.current_stream().synchronize()
+        return unsm, planes
+
+    # -- superpixels -----------------------------------------------------------------------------
+    def _slots(self, slots, n):
+        if slots is None:
+            return None, None
+        a = np.ascontiguousarray(slots, dtype=np.int32)
+        assert a.size == n
+        return a, C.c_void_p(a.ctypes.data)
+
+    def superpixels_reset(self, n=1, slots=None) -> int:
+        keep, sp = self._slots(slots, n)
+        ml = C.c_int()
+        self._check(_lib.cartb200_superpixels_reset(self._h, n, sp, C.byref(ml), self._stream()))
+        self.torch.cuda.current_stream().synchronize()
+        return ml.value
+
+    def superpixels_relax(self, left, deriv, iterations, slots=None):
+        torch = self.torch
+        n, lp, pitch, fs = self._img(left, torch.uint8, 3)
+        keep, sp = self._slots(slots, n)
+        if deriv is not None:
+            n2, dp, dpitch, dfs = self._img(deriv, torch.int16, 2)
+            assert n2 == n
+        else:
+            dp, dpitch, dfs = None, 0, 0
+        out = torch.empty((n, self.H, self.W), dtype=torch.uint16, device=left.device)
+        self._check(_lib.cartb200_superpixels_relax(self._h, n, sp, iterations, lp, pitch, fs, dp, dpitch, dfs,
+                                                    out.data_ptr(), self.W * 2, self.W * self.H * 2, self._stream()))
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    def superpixels_set_labels(self, slot, labels):
+        torch = self.torch
+        assert labels.is_cuda and labels.dtype == torch.uint16 and labels.shape == (self.H, self.W) and labels.is_contiguous()
+        self._check(_lib.cartb200_superpixels_set_labels(self._h, slot, labels.data_ptr(), self.W * 2, self._stream()))
+
+    def superpixels_border_map(self, labels):
+        torch = self.torch
+        assert labels.is_cuda and labels.dtype == torch.uint16 and labels.shape == (self.H, self.W) and labels.is_contiguous()
+        out = torch.empty((self.H, self.W), dtype=torch.uint8, device=labels.device)
+        self._check(_lib.cartb200_superpixels_border_map(self._h, labels.data_ptr(), self.W * 2, out.data_ptr(), self.W,
+                                                         self._stream()))
+        return out
+
+    # -- whole sequence --------------------------------------------------------------------------
+    def run_sequence_host(self, opts: SequenceOptions, left, right, want_disparity=False, planes_out=None,
+                          disparity_out=None):
+        """left/right: host uint8 [n,H,W,3] (numpy arrays or pinned CPU torch tensors). Returns numpy planes."""
+        def ptr(a):
+            if isinstance(a, np.ndarray):
+                assert a.flags.c_contiguous
+                return a.ctypes.data
+            return a.data_ptr()
+        n = left.shape[0]
+        assert tuple(left.shape) == (n, self.H, self.W, 3) and tuple(right.shape) == tuple(left.shape)
+        if planes_out is None:
+            planes_out = np.empty((n, self.H, self.W), np.uint8)
+        if want_disparity and disparity_out is None:
+            disparity_out = np.empty((n, self.H, self.W), np.int16)
+        o = opts.to_c()
+        self._check(_lib.cartb200_run_sequence_host(self._h, C.byref(o), n, ptr(left), ptr(right), ptr(planes_out),
+                                                    ptr(disparity_out) if disparity_out is not None else None))
+        return (planes_out, disparity_out) if want_disparity else planes_out
+
+    def run_sequence_device(self, opts: SequenceOptions, left, right, want_disparity=False, planes_out=None):
+        torch = self.torch
+        n, lp, pitch, fs = self._img(left, torch.uint8, 3)
+        _, rp, _, _ = self._img(right, torch.uint8, 3)
+        assert pitch == self.W * 3 and fs == self.W * self.H * 3, "device sequence buffers must be tightly packed"
+        if planes_out is None:
+            planes_out = torch.empty((n, self.H, self.W), dtype=torch.uint8, device=left.device)
+        disp = torch.empty((n, self.H, self.W), dtype=torch.int16, device=left.device) if want_disparity else None
+        o = opts.to_c()
+        self._check(_lib.cartb200_run_sequence_device(self._h, C.byref(o), n, lp, rp, planes_out.data_ptr(),
+                                                      disp.data_ptr() if disp is not None else None, self._stream()))
+        return (planes_out, disp) if want_disparity else planes_out

@@ -1,0 +1,787 @@
+// C ABI of libcartb200 (include/cartb200.h): context management, argument validation, stage entry
+// points and the whole-sequence runner that reproduces the reference's per-sequence state.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "tile_ref.cuh"
+
+namespace cb {
+uint32_t debug_median9_host(const uint16_t* v9);
+int histogram_peak_update(const int32_t* hist, int32_t* params);  // plane_params.cpp
+}  // namespace cb
+
+using namespace cb;
+
+namespace {
+
+struct SeqScratch {
+    int nFrames = 0, pipeline = -1;
+    uint8_t* inL = nullptr;     // staged inputs (host variant) [n][H][W*3]
+    uint8_t* inR = nullptr;
+    int16_t* disp = nullptr;    // [B] or [n] frames, tight pitch
+    int16_t* deriv = nullptr;   // pipeline 0: [B] s16; pipeline 1: [n] s16x2
+    uint16_t* labels = nullptr; // pipeline 1: [n]
+    uint8_t* planes = nullptr;  // [n]
+    uint8_t* unsm = nullptr;    // [B]
+    int32_t* hist = nullptr;    // [n][512]
+    int32_t* histHost = nullptr;  // pinned
+    int32_t* paramsHost = nullptr;  // pinned [n][4]
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evIn[2] = {nullptr, nullptr};
+    size_t inCap = 0, inRCap = 0, dispCap = 0, derivCap = 0, labelsCap = 0, planesCap = 0, histCap = 0, unsmCap = 0;
+};
+
+template <typename T>
+int devAlloc(cartb200_ctx* c, T** p, size_t bytes) {
+    if (cudaMalloc((void**)p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        c->err = "cudaMalloc of " + std::to_string(bytes) + " bytes failed";
+        return CARTB200_E_NOMEM;
+    }
+    c->scratchBytes += bytes;
+    return CARTB200_OK;
+}
+
+template <typename T>
+int ensureCap(cartb200_ctx* c, T** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return CARTB200_OK;
+    if (*p) {
+        cudaFree(*p);
+        c->scratchBytes -= *cap;
+        *p = nullptr;
+        *cap = 0;
+    }
+    int rc = devAlloc(c, p, bytes);
+    if (rc == CARTB200_OK) *cap = bytes;
+    return rc;
+}
+
+int* slotIota(cartb200_ctx* c) { return reinterpret_cast<int*>(c->paramsDev + 4 * (size_t)c->B); }
+int* slotScratch(cartb200_ctx* c) { return slotIota(c) + c->B; }
+
+int checkBatch(cartb200_ctx* c, int n) {
+    if (!c) return CARTB200_E_ARG;
+    if (n < 1 || n > c->B) {
+        c->err = "batch size " + std::to_string(n) + " outside 1.." + std::to_string(c->B);
+        return CARTB200_E_ARG;
+    }
+    return CARTB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cartb200_version(void) { return "cartb200 0.1 (sm_100a)"; }
+
+void cartb200_default_config(cartb200_config* cfg, int width, int height) {
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->width = width;
+    cfg->height = height;
+    cfg->max_batch = 1;
+    cfg->min_disparity = 4;       // cartconfig.cpp:147
+    cfg->num_disparities = 256;   // cartconfig.cpp:148
+    cfg->p1 = 10;                 // cv::cuda::createStereoSGM defaults
+    cfg->p2 = 120;
+    cfg->uniqueness_ratio = 12;   // disparity.hpp:32
+    cfg->paths = 4;               // MODE_HH4
+    cfg->smoothing_radius = -1;   // cartconfig.cpp:150
+    cfg->smoothing_iterations = 5;
+    cfg->enable_superpixels = 1;
+    cfg->sp_block_size = 12;                 // cartconfig.cpp:126
+    cfg->sp_direct_clique_cost = 0.5;        // :128
+    cfg->sp_diagonal_clique_cost = 0.5 / 1.4142135623730951;  // :129
+    cfg->sp_compactness_weight = 0.1;        // :130
+    cfg->sp_progressive_compactness_cost = 0.0;
+    cfg->sp_image_weight = 1.5;              // :132
+    cfg->sp_disparity_weight = 1.0;          // :133
+}
+
+void cartb200_default_sequence_opts(cartb200_sequence_opts* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->pipeline = 0;
+    o->provider = 1;
+    o->update_interval = 30;  // cartconfig.cpp:202
+    o->reset_interval = 10;   // :203
+    o->sp_initial_iterations = 18;
+    o->sp_iterations = 6;
+    o->sp_reset_iterations = 64;
+    o->start_id = 1;
+}
+
+int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
+    if (!cfg || !out) return CARTB200_E_ARG;
+    *out = nullptr;
+    cartb200_ctx* c = new (std::nothrow) cartb200_ctx();
+    if (!c) return CARTB200_E_NOMEM;
+    c->cfg = *cfg;
+    auto fail = [&](int rc) {
+        // keep the message reachable: the caller cannot read it from a destroyed context, so print it
+        fprintf(stderr, "cartb200_create: %s\n", c->err.c_str());
+        cartb200_destroy(c);
+        return rc;
+    };
+    if (cfg->width < 16 || cfg->height < 8 || cfg->max_batch < 1) {
+        c->err = "invalid size / batch";
+        return fail(CARTB200_E_ARG);
+    }
+    if (cfg->num_disparities != 64 && cfg->num_disparities != 128 && cfg->num_disparities != 256) {
+        c->err = "num_disparities must be 64, 128 or 256 (cv::cuda::StereoSGM restriction)";
+        return fail(CARTB200_E_UNSUPPORTED);
+    }
+    if (cfg->paths != 4 && cfg->paths != 8) {
+        c->err = "paths must be 4 (MODE_HH4) or 8 (MODE_HH)";
+        return fail(CARTB200_E_UNSUPPORTED);
+    }
+    if (cfg->p1 < 0 || cfg->p2 < cfg->p1 || 31 + cfg->p2 > 255) {
+        c->err = "need 0 <= p1 <= p2 and 31 + p2 <= 255 (u8 path volumes)";
+        return fail(CARTB200_E_UNSUPPORTED);
+    }
+    int dev = 0, ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        c->err = "no CUDA device: the cartb200 path has no CPU fallback";
+        return fail(CARTB200_E_CUDA);
+    }
+    cudaGetDevice(&dev);
+    c->W = cfg->width;
+    c->H = cfg->height;
+    c->D = cfg->num_disparities;
+    c->B = cfg->max_batch;
+    c->P = cfg->paths;
+    const size_t W = c->W, H = c->H, B = c->B;
+    int rc;
+    c->grayPitch = alignUp(W, 128);
+    c->censusPitch = alignUp(W * 4, 128);
+    c->dispPitch = alignUp(W * 2, 128);
+    c->volFrameStride = H * W * (size_t)c->D;
+    c->volPathStride = c->volFrameStride * B;
+    if ((rc = devAlloc(c, &c->grayL, B * H * c->grayPitch))) return fail(rc);
+    if ((rc = devAlloc(c, &c->censusL, B * H * c->censusPitch))) return fail(rc);
+    if ((rc = devAlloc(c, &c->censusR, B * H * c->censusPitch))) return fail(rc);
+    if ((rc = devAlloc(c, &c->volumes, c->volPathStride * c->P))) return fail(rc);
+    if ((rc = devAlloc(c, &c->wtaL, B * H * c->dispPitch))) return fail(rc);
+    if ((rc = devAlloc(c, &c->wtaR, B * H * c->dispPitch))) return fail(rc);
+    if ((rc = devAlloc(c, &c->medL, B * H * c->dispPitch))) return fail(rc);
+    // paramsDev [B][4] + slot iota [B] + slot scratch [B]
+    if ((rc = devAlloc(c, &c->paramsDev, (4 * B + 2 * B) * sizeof(int32_t)))) return fail(rc);
+    {
+        std::vector<int> iota(B);
+        for (size_t i = 0; i < B; ++i) iota[i] = (int)i;
+        if (cudaMemcpy(slotIota(c), iota.data(), B * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+            c->err = "cudaMemcpy failed";
+            return fail(CARTB200_E_CUDA);
+        }
+    }
+    if (cfg->enable_superpixels) {
+        if (cfg->sp_block_size < 1) {
+            c->err = "blockSize must be more than 1";  // superpixels.cu:36-38
+            return fail(CARTB200_E_ARG);
+        }
+        if (cfg->sp_direct_clique_cost < 0 || cfg->sp_compactness_weight < 0 || cfg->sp_image_weight < 0 ||
+            cfg->sp_disparity_weight < 0) {
+            c->err = "clique cost / weights must be non-negative";  // superpixels.cu:40-46
+            return fail(CARTB200_E_ARG);
+        }
+        c->spBlocksPerRow = ceilDiv(c->W, cfg->sp_block_size);
+        c->maxLabels = c->spBlocksPerRow * ceilDiv(c->H, cfg->sp_block_size);
+        if (c->maxLabels >= (1 << 14)) {
+            c->err = "superpixel count must stay below 16384 (OUT_OF_BOUNDS marker, contourrelaxation.cu:21)";
+            return fail(CARTB200_E_UNSUPPORTED);
+        }
+        c->spLabelPitch = alignUp(W * 2, 128);
+        if ((rc = devAlloc(c, &c->spLabels, B * H * c->spLabelPitch))) return fail(rc);
+        if ((rc = devAlloc(c, &c->spYcc, B * H * W * 4))) return fail(rc);
+        if ((rc = devAlloc(c, &c->spStats, B * (size_t)(c->maxLabels + 1) * 24 * sizeof(double)))) return fail(rc);
+        if ((rc = devAlloc(c, &c->spNew, B * H * W * sizeof(uint16_t)))) return fail(rc);
+        if ((rc = devAlloc(c, &c->votes, B * (size_t)c->maxLabels * 4 * sizeof(uint32_t)))) return fail(rc);
+        if ((rc = launch_sp_reset(c, c->B, nullptr, nullptr))) return fail(rc);
+        if (cudaDeviceSynchronize() != cudaSuccess) {
+            c->err = "superpixel initialisation failed";
+            return fail(CARTB200_E_CUDA);
+        }
+    }
+    *out = c;
+    return CARTB200_OK;
+}
+
+void cartb200_destroy(cartb200_ctx* c) {
+    if (!c) return;
+    cudaFree(c->grayL);
+    cudaFree(c->grayR);
+    cudaFree(c->censusL);
+    cudaFree(c->censusR);
+    cudaFree(c->volumes);
+    cudaFree(c->wtaL);
+    cudaFree(c->wtaR);
+    cudaFree(c->medL);
+    cudaFree(c->medR);
+    cudaFree(c->paramsDev);
+    cudaFree(c->votes);
+    cudaFree(c->spLabels);
+    cudaFree(c->spYcc);
+    cudaFree(c->spStats);
+    cudaFree(c->spNew);
+    if (c->seq) {
+        SeqScratch* q = static_cast<SeqScratch*>(c->seq);
+        cudaFree(q->inL);
+        cudaFree(q->inR);
+        cudaFree(q->disp);
+        cudaFree(q->deriv);
+        cudaFree(q->labels);
+        cudaFree(q->planes);
+        cudaFree(q->unsm);
+        cudaFree(q->hist);
+        cudaFreeHost(q->histHost);
+        cudaFreeHost(q->paramsHost);
+        if (q->copyStream) cudaStreamDestroy(q->copyStream);
+        for (auto& e : q->evIn)
+            if (e) cudaEventDestroy(e);
+        delete q;
+    }
+    cudaGetLastError();
+    delete c;
+}
+
+const char* cartb200_last_error(const cartb200_ctx* c) { return c ? c->err.c_str() : "null context"; }
+long long cartb200_launch_count(const cartb200_ctx* c) { return c ? c->launches : 0; }
+size_t cartb200_scratch_bytes(const cartb200_ctx* c) { return c ? c->scratchBytes : 0; }
+
+// ---- disparity ---------------------------------------------------------------------------------
+int cartb200_sgm_gray_census(cartb200_ctx* c, int n, const uint8_t* l, const uint8_t* r, size_t pitch, size_t fstride,
+                             void* stream) {
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    if (!l || !r || pitch < (size_t)c->W * 3) {
+        c->err = "gray_census: bad image arguments";
+        return CARTB200_E_ARG;
+    }
+    return launch_gray_census(c, n, ImgBatch<const uint8_t>{l, pitch, fstride}, ImgBatch<const uint8_t>{r, pitch, fstride},
+                              (cudaStream_t)stream);
+}
+
+int cartb200_sgm_aggregate(cartb200_ctx* c, int n, void* stream) {
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    return launch_aggregate(c, n, (cudaStream_t)stream);
+}
+
+int cartb200_interpolate(cartb200_ctx* c, int n, int16_t* d, size_t pitch, size_t fstride, int radius, int iterations,
+                         int minD, int maxD, void* stream) {
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    if (!d || pitch < (size_t)c->W * 2) {
+        c->err = "interpolate: bad image arguments";
+        return CARTB200_E_ARG;
+    }
+    return launch_interpolate(c, n, ImgBatch<int16_t>{d, pitch, fstride}, radius, iterations, minD, maxD,
+                              (cudaStream_t)stream);
+}
+
+int cartb200_sgm_wta_post(cartb200_ctx* c, int n, int16_t* d, size_t pitch, size_t fstride, void* stream) {
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    if (!d || pitch < (size_t)c->W * 2) {
+        c->err = "wta_post: bad image arguments";
+        return CARTB200_E_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = launch_wta(c, n, s))) return rc;
+    ImgBatch<int16_t> out{d, pitch, fstride};
+    if ((rc = launch_sgm_post(c, n, out, s))) return rc;
+    if (c->cfg.smoothing_radius > 0) {
+        // ImageDisparityModule passes minDisparity*16 and the image width (disparity.hpp:27-28, disparity.cu:74)
+        rc = launch_interpolate(c, n, out, c->cfg.smoothing_radius, c->cfg.smoothing_iterations,
+                                c->cfg.min_disparity * 16, c->W, s);
+    }
+    return rc;
+}
+
+int cartb200_disparity(cartb200_ctx* c, int n, const uint8_t* l, const uint8_t* r, size_t pitch, size_t fstride,
+                       int16_t* d, size_t dpitch, size_t dfstride, void* stream) {
+    int rc;
+    if ((rc = cartb200_sgm_gray_census(c, n, l, r, pitch, fstride, stream))) return rc;
+    if ((rc = cartb200_sgm_aggregate(c, n, stream))) return rc;
+    return cartb200_sgm_wta_post(c, n, d, dpitch, dfstride, stream);
+}
+
+int cartb200_sgm_intermediate(cartb200_ctx* c, int which, const void** ptr, size_t* pitch, size_t* fstride) {
+    if (!c || !ptr || !pitch || !fstride) return CARTB200_E_ARG;
+    const size_t H = c->H;
+    switch (which) {
+        case 0: *ptr = c->censusL; *pitch = c->censusPitch; *fstride = c->censusPitch * H; return CARTB200_OK;
+        case 1: *ptr = c->censusR; *pitch = c->censusPitch; *fstride = c->censusPitch * H; return CARTB200_OK;
+        case 2: *ptr = c->grayL; *pitch = c->grayPitch; *fstride = c->grayPitch * H; return CARTB200_OK;
+        case 3: *ptr = c->wtaL; *pitch = c->dispPitch; *fstride = c->dispPitch * H; return CARTB200_OK;
+        case 4: *ptr = c->wtaR; *pitch = c->dispPitch; *fstride = c->dispPitch * H; return CARTB200_OK;
+        default:
+            if (which >= 10 && which < 10 + c->P) {
+                *ptr = c->volumes + (size_t)(which - 10) * c->volPathStride;
+                *pitch = (size_t)c->W * c->D;
+                *fstride = c->volFrameStride;
+                return CARTB200_OK;
+            }
+    }
+    c->err = "sgm_intermediate: unknown selector";
+    return CARTB200_E_ARG;
+}
+
+// ---- derivative / planeseg ---------------------------------------------------------------------
+int cartb200_derivative(cartb200_ctx* c, int n, const int16_t* d, size_t dp, size_t dfs, int16_t* o, size_t op,
+                        size_t ofs, int32_t* hist, void* stream) {
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    if (!d || !o || !hist || dp < (size_t)c->W * 2 || op < (size_t)c->W * 4 || (op & 3)) {
+        c->err = "derivative: bad image arguments (derivative pitch must be a multiple of 4)";
+        return CARTB200_E_ARG;
+    }
+    return launch_derivative(c, n, ImgBatch<const int16_t>{d, dp, dfs}, ImgBatch<int16_t>{o, op, ofs}, hist,
+                             (cudaStream_t)stream);
+}
+
+int cartb200_naive_derivative(cartb200_ctx* c, int n, const int16_t* d, size_t dp, size_t dfs, int16_t* o, size_t op,
+                              size_t ofs, int32_t* hist, void* stream) {
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    if (!d || !o || !hist || dp < (size_t)c->W * 2 || op < (size_t)c->W * 2) {
+        c->err = "naive_derivative: bad image arguments";
+        return CARTB200_E_ARG;
+    }
+    return launch_naive_derivative(c, n, ImgBatch<const int16_t>{d, dp, dfs}, ImgBatch<int16_t>{o, op, ofs}, hist,
+                                   (cudaStream_t)stream);
+}
+
+static int uploadParams(cartb200_ctx* c, int n, const int32_t* paramsHost, cudaStream_t s) {
+    if (!paramsHost) {
+        c->err = "plane parameters missing";
+        return CARTB200_E_ARG;
+    }
+    CB_CHECK_CUDA(c, cudaMemcpyAsync(c->paramsDev, paramsHost, (size_t)n * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    return CARTB200_OK;
+}
+
+int cartb200_classify(cartb200_ctx* c, int n, const int16_t* d, size_t dp, size_t dfs, int channels, int channel,
+                      const int32_t* paramsHost, uint8_t* planes, size_t pp, size_t pfs, void* stream) {
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    if (!d || !planes || channels < 1 || channel < 0 || channel >= channels || dp < (size_t)c->W * 2 * channels ||
+        pp < (size_t)c->W) {
+        c->err = "classify: bad arguments";
+        return CARTB200_E_ARG;
+    }
+    if ((rc = uploadParams(c, n, paramsHost, (cudaStream_t)stream))) return rc;
+    return launch_classify(c, n, ImgBatch<const int16_t>{d, dp, dfs}, channels, channel, c->paramsDev,
+                           ImgBatch<uint8_t>{planes, pp, pfs}, (cudaStream_t)stream);
+}
+
+int cartb200_sp_planeseg(cartb200_ctx* c, int n, const int16_t* d, size_t dp, size_t dfs, const uint16_t* labels,
+                         size_t lp, size_t lfs, int maxLabel, const int32_t* paramsHost, uint8_t* unsm, uint8_t* planes,
+                         size_t pp, size_t pfs, void* stream) {
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    if (!c->votes) {
+        c->err = "sp_planeseg: context created without superpixels";
+        return CARTB200_E_ARG;
+    }
+    if (!d || !labels || !unsm || !planes || dp < (size_t)c->W * 4 || lp < (size_t)c->W * 2 || pp < (size_t)c->W ||
+        maxLabel < 1 || maxLabel > c->maxLabels) {
+        c->err = "sp_planeseg: bad arguments";
+        return CARTB200_E_ARG;
+    }
+    if ((size_t)(maxLabel + 1) * 3 * sizeof(uint16_t) > 32768) {  // sp_planeseg.cu:327-331
+        c->err = "Shared memory size exceeds maximum. Reduce image size or increase block size.";
+        return CARTB200_E_UNSUPPORTED;
+    }
+    if ((rc = uploadParams(c, n, paramsHost, (cudaStream_t)stream))) return rc;
+    return launch_sp_planeseg(c, n, ImgBatch<const int16_t>{d, dp, dfs}, ImgBatch<const uint16_t>{labels, lp, lfs},
+                              maxLabel, c->paramsDev, ImgBatch<uint8_t>{unsm, pp, pfs}, ImgBatch<uint8_t>{planes, pp, pfs},
+                              (cudaStream_t)stream);
+}
+
+int cartb200_histogram_peak_update(const int32_t* hist, int32_t* params) {
+    if (!hist || !params) return CARTB200_E_ARG;
+    return cb::histogram_peak_update(hist, params);
+}
+
+// ---- superpixels -------------------------------------------------------------------------------
+static int resolveSlots(cartb200_ctx* c, int n, const int* slotsHost, const int** dev, cudaStream_t s) {
+    if (!c->spLabels) {
+        c->err = "context created without superpixels";
+        return CARTB200_E_ARG;
+    }
+    if (!slotsHost) {
+        *dev = slotIota(c);
+        return CARTB200_OK;
+    }
+    for (int i = 0; i < n; ++i)
+        if (slotsHost[i] < 0 || slotsHost[i] >= c->B) {
+            c->err = "slot id out of range";
+            return CARTB200_E_ARG;
+        }
+    CB_CHECK_CUDA(c, cudaMemcpyAsync(slotScratch(c), slotsHost, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    *dev = slotScratch(c);
+    return CARTB200_OK;
+}
+
+int cartb200_superpixels_reset(cartb200_ctx* c, int n, const int* slotsHost, int* maxLabelOut, void* stream) {
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    const int* dev;
+    if ((rc = resolveSlots(c, n, slotsHost, &dev, (cudaStream_t)stream))) return rc;
+    if (maxLabelOut) *maxLabelOut = c->maxLabels;
+    return launch_sp_reset(c, n, dev, (cudaStream_t)stream);
+}
+
+int cartb200_superpixels_relax(cartb200_ctx* c, int n, const int* slotsHost, int iterations, const uint8_t* bgr,
+                               size_t bp, size_t bfs, const int16_t* deriv, size_t dp, size_t dfs, uint16_t* out,
+                               size_t op, size_t ofs, void* stream) {
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    const int* dev;
+    if ((rc = resolveSlots(c, n, slotsHost, &dev, (cudaStream_t)stream))) return rc;
+    if (!bgr || bp < (size_t)c->W * 3 || iterations < 0 || (deriv && (dp < (size_t)c->W * 4)) ||
+        (out && op < (size_t)c->W * 2)) {
+        c->err = "superpixels_relax: bad arguments";
+        return CARTB200_E_ARG;
+    }
+    return launch_sp_relax(c, n, dev, iterations, ImgBatch<const uint8_t>{bgr, bp, bfs},
+                           ImgBatch<const int16_t>{deriv, dp, dfs}, deriv != nullptr, ImgBatch<uint16_t>{out, op, ofs},
+                           (cudaStream_t)stream);
+}
+
+int cartb200_superpixels_set_labels(cartb200_ctx* c, int slot, const uint16_t* labels, size_t lp, void* stream) {
+    if (!c || !c->spLabels || slot < 0 || slot >= c->B || !labels || lp < (size_t)c->W * 2) {
+        if (c) c->err = "superpixels_set_labels: bad arguments";
+        return CARTB200_E_ARG;
+    }
+    CB_CHECK_CUDA(c, cudaMemcpy2DAsync((char*)c->spLabels + (size_t)slot * c->spLabelPitch * c->H, c->spLabelPitch, labels,
+                                       lp, (size_t)c->W * 2, c->H, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CARTB200_OK;
+}
+
+int cartb200_superpixels_border_map(cartb200_ctx* c, const uint16_t* labels, size_t lp, uint8_t* border, size_t bp,
+                                    void* stream) {
+    if (!c || !labels || !border || lp < (size_t)c->W * 2 || bp < (size_t)c->W) {
+        if (c) c->err = "border_map: bad arguments";
+        return CARTB200_E_ARG;
+    }
+    return launch_border_map(c, Img<const uint16_t>{labels, lp}, Img<uint8_t>{border, bp}, (cudaStream_t)stream);
+}
+
+// ---- debug helpers (CPU, no GPU needed) --------------------------------------------------------
+struct HostI32 {
+    const int32_t* p;
+    int W;
+    int32_t operator()(int x, int y) const { return p[(size_t)y * W + x]; }
+};
+
+int32_t cartb200_debug_ref_tile_i32(const int32_t* img, int W, int H, int bx, int by, int bdx, int bdy, int XB, int YB,
+                                    int yPad, int xPad, int interp, long alloc, int32_t undef, int lx, int ly) {
+    TileGeom g{W, H, bdx * XB, bdy * YB, xPad, yPad, XB, YB, alloc};
+    HostI32 acc{img, W};
+    TileEval<int32_t, HostI32> te(acc, g, bx, by, undef);
+    return interp ? te.value<true>(lx, ly) : te.value<false>(lx, ly);
+}
+
+uint32_t cartb200_debug_median9(const uint16_t* v9) { return cb::debug_median9_host(v9); }
+
+}  // extern "C"
+
+// =================================================================================================
+// Whole-sequence runner.  Reproduces, for frames processed in id order, the state the reference's
+// modules carry across frames:
+//   * SuperPixelModule: label image warm-started from the previous frame, re-blocked when
+//     id % reset == 0, `initial` iterations on id == 1 or id % reset == 0 (superpixels.cu:93-113);
+//   * DisparityPlaneSegmentationModule: running histogram, parameter update when id % update == 1,
+//     zeroed after the download when id % (update*reset) == 1 (planeseg.cu:379-403);
+//   * SuperPixelDisparityPlaneSegmentationModule: first call creates a zero running histogram without
+//     adding the frame, then accumulate / maybe reset / update (sp_planeseg.cu:352-388).
+// The superpixel chain is the only true frame-to-frame dependency, and it is cut at every reset, so the
+// sequence is processed as independent chunks [k*reset, (k+1)*reset) advanced in lock step: step s
+// handles frame k*reset + s of every chunk k in one batched launch.
+namespace {
+
+struct HistState {
+    bool created = false;
+    std::vector<long long> running = std::vector<long long>(256, 0);
+    int32_t params[6] = {0, 0, 0, 0, 0, 0};  // hC, vC, hS, hE, vS, vE
+};
+
+// naive module bookkeeping for frame `id` whose own histogram is `h`; writes the ranges to use
+void naiveUpdate(HistState& st, const cartb200_sequence_opts& o, int id, const int32_t* h, int32_t* outParams) {
+    for (int i = 0; i < 256; ++i) st.running[i] += h[i];  // mergeHistogram (planeseg.cu:144-158)
+    if (o.provider == 1 && id % o.update_interval == 1) {
+        int32_t snap[256];
+        for (int i = 0; i < 256; ++i) snap[i] = (int32_t)st.running[i];
+        if (id % (o.update_interval * o.reset_interval) == 1) std::fill(st.running.begin(), st.running.end(), 0);
+        cb::histogram_peak_update(snap, st.params);
+    }
+    std::memcpy(outParams, st.params + 2, 4 * sizeof(int32_t));
+}
+
+// SP module bookkeeping; h = vertical channel of the frame's derivative histogram
+void spUpdate(HistState& st, const cartb200_sequence_opts& o, int id, const int32_t* hv, int32_t* outParams) {
+    int32_t hist[256];
+    if (!st.created) {
+        st.created = true;  // zeros; the first frame is NOT added (sp_planeseg.cu:364-366)
+        for (int i = 0; i < 256; ++i) hist[i] = hv[i];
+    } else {
+        for (int i = 0; i < 256; ++i) {
+            st.running[i] += hv[i];
+            hist[i] = (int32_t)st.running[i];
+        }
+    }
+    if (id % (o.update_interval * o.reset_interval) == 1) std::fill(st.running.begin(), st.running.end(), 0);
+    if (o.provider == 1 && id % o.update_interval == 1) cb::histogram_peak_update(hist, st.params);
+    std::memcpy(outParams, st.params + 2, 4 * sizeof(int32_t));
+}
+
+int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const uint8_t* inL, const uint8_t* inR,
+                bool inputsOnHost, uint8_t* planesOut, int16_t* dispOut, bool outputsOnHost, cudaStream_t userStream) {
+    if (!c || !o || n < 1 || !inL || !inR || !planesOut) {
+        if (c) c->err = "run_sequence: bad arguments";
+        return CARTB200_E_ARG;
+    }
+    if (o->pipeline != 0 && o->pipeline != 1) {
+        c->err = "run_sequence: unknown pipeline";
+        return CARTB200_E_ARG;
+    }
+    if (o->update_interval < 1 || o->reset_interval < 1) {
+        c->err = "run_sequence: intervals must be >= 1";
+        return CARTB200_E_ARG;
+    }
+    const int R = o->sp_reset_iterations;
+    if (o->pipeline == 1) {
+        if (!c->spLabels) {
+            c->err = "run_sequence: superpixel pipeline needs enable_superpixels";
+            return CARTB200_E_ARG;
+        }
+        if (R < 1 || !(o->start_id == 1 || o->start_id % R == 0)) {
+            c->err = "run_sequence: the superpixel chain can only start at id 1 or at a reset frame";
+            return CARTB200_E_UNSUPPORTED;
+        }
+    }
+    if (!c->seq) c->seq = new SeqScratch();
+    SeqScratch* q = static_cast<SeqScratch*>(c->seq);
+    const size_t W = c->W, H = c->H, B = c->B;
+    const size_t bgrFrame = W * H * 3, pxFrame = W * H;
+    int rc;
+    cudaStream_t s = userStream;
+    if (!q->copyStream) {
+        CB_CHECK_CUDA(c, cudaStreamCreateWithFlags(&q->copyStream, cudaStreamNonBlocking));
+        for (auto& e : q->evIn) CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const bool peak = o->provider == 1;
+    const bool sp = o->pipeline == 1;
+    // storage
+    if (inputsOnHost) {
+        if ((rc = ensureCap(c, &q->inL, &q->inCap, bgrFrame * n))) return rc;
+        if ((rc = ensureCap(c, &q->inR, &q->inRCap, bgrFrame * n))) return rc;
+    }
+    const size_t nStore = (sp && peak) ? (size_t)n : B;  // frames whose derivative/labels must be kept
+    if ((rc = ensureCap(c, &q->disp, &q->dispCap, pxFrame * 2 * (dispOut ? (size_t)n : B)))) return rc;
+    if ((rc = ensureCap(c, &q->deriv, &q->derivCap, pxFrame * (sp ? 4 : 2) * nStore))) return rc;
+    if (sp && (rc = ensureCap(c, &q->labels, &q->labelsCap, pxFrame * 2 * nStore))) return rc;
+    if ((rc = ensureCap(c, &q->planes, &q->planesCap, pxFrame * (size_t)n))) return rc;
+    if (sp && (rc = ensureCap(c, &q->unsm, &q->unsmCap, pxFrame * B))) return rc;
+    if ((rc = ensureCap(c, &q->hist, &q->histCap, (size_t)n * 512 * sizeof(int32_t)))) return rc;
+    if (q->nFrames < n) {
+        cudaFreeHost(q->histHost);
+        cudaFreeHost(q->paramsHost);
+        CB_CHECK_CUDA(c, cudaMallocHost((void**)&q->histHost, (size_t)n * 512 * sizeof(int32_t)));
+        CB_CHECK_CUDA(c, cudaMallocHost((void**)&q->paramsHost, (size_t)n * 4 * sizeof(int32_t)));
+        q->nFrames = n;
+    }
+    uint8_t* planesDev = outputsOnHost ? q->planes : planesOut;
+    int16_t* dispDev = dispOut ? (outputsOnHost ? q->disp : dispOut) : q->disp;
+    const uint8_t* devL = inputsOnHost ? q->inL : inL;
+    const uint8_t* devR = inputsOnHost ? q->inR : inR;
+
+    HistState hs;
+    if (!peak) {
+        hs.params[2] = o->static_params[0];
+        hs.params[3] = o->static_params[1];
+        hs.params[4] = o->static_params[2];
+        hs.params[5] = o->static_params[3];
+    }
+
+    if (!sp) {
+        // ---------------- naive pipeline: disparity -> naive derivative/hist -> params -> classify ----
+        // inputs are uploaded batch by batch on the copy stream, one batch ahead of the compute
+        auto upload = [&](int b0) -> int {
+            if (!inputsOnHost || b0 >= n) return CARTB200_OK;
+            const int nb = std::min<int>((int)B, n - b0);
+            CB_CHECK_CUDA(c, cudaMemcpyAsync(q->inL + bgrFrame * b0, inL + bgrFrame * b0, bgrFrame * nb,
+                                             cudaMemcpyHostToDevice, q->copyStream));
+            CB_CHECK_CUDA(c, cudaMemcpyAsync(q->inR + bgrFrame * b0, inR + bgrFrame * b0, bgrFrame * nb,
+                                             cudaMemcpyHostToDevice, q->copyStream));
+            CB_CHECK_CUDA(c, cudaEventRecord(q->evIn[(b0 / B) & 1], q->copyStream));
+            return CARTB200_OK;
+        };
+        if ((rc = upload(0))) return rc;
+        for (int b0 = 0; b0 < n; b0 += (int)B) {
+            const int nb = std::min<int>((int)B, n - b0);
+            if (inputsOnHost) CB_CHECK_CUDA(c, cudaStreamWaitEvent(s, q->evIn[(b0 / B) & 1], 0));
+            if ((rc = upload(b0 + (int)B))) return rc;
+            int16_t* dB = dispOut ? dispDev + pxFrame * b0 : dispDev;
+            if ((rc = cartb200_disparity(c, nb, devL + bgrFrame * b0, devR + bgrFrame * b0, W * 3, bgrFrame, dB, W * 2,
+                                         pxFrame * 2, s)))
+                return rc;
+            if ((rc = launch_naive_derivative(c, nb, ImgBatch<const int16_t>{dB, W * 2, pxFrame * 2},
+                                              ImgBatch<int16_t>{q->deriv, W * 2, pxFrame * 2}, q->hist + 256 * (size_t)b0, s)))
+                return rc;
+            int32_t* ph = q->paramsHost + 4 * (size_t)b0;
+            if (peak) {
+                CB_CHECK_CUDA(c, cudaMemcpyAsync(q->histHost + 256 * (size_t)b0, q->hist + 256 * (size_t)b0,
+                                                 (size_t)nb * 256 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+                CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
+                for (int i = 0; i < nb; ++i)
+                    naiveUpdate(hs, *o, o->start_id + b0 + i, q->histHost + 256 * (size_t)(b0 + i), ph + 4 * i);
+            } else {
+                for (int i = 0; i < nb; ++i) std::memcpy(ph + 4 * i, hs.params + 2, 4 * sizeof(int32_t));
+            }
+            if ((rc = uploadParams(c, nb, ph, s))) return rc;
+            if ((rc = launch_classify(c, nb, ImgBatch<const int16_t>{q->deriv, W * 2, pxFrame * 2}, 1, 0, c->paramsDev,
+                                      ImgBatch<uint8_t>{planesDev + pxFrame * b0, W, pxFrame}, s)))
+                return rc;
+            if (outputsOnHost) {
+                CB_CHECK_CUDA(c, cudaMemcpyAsync(planesOut + pxFrame * b0, planesDev + pxFrame * b0, pxFrame * nb,
+                                                 cudaMemcpyDeviceToHost, s));
+                if (dispOut)
+                    CB_CHECK_CUDA(c, cudaMemcpyAsync(dispOut + pxFrame * b0, dB, pxFrame * 2 * nb, cudaMemcpyDeviceToHost, s));
+            }
+        }
+        if (outputsOnHost || inputsOnHost) CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
+        return CARTB200_OK;
+    }
+
+    // ---------------- superpixel pipeline ------------------------------------------------------------
+    // virtual ids: chunk k covers ids [k*R, k*R + R); frame index (0-based) = id - start_id.
+    if (inputsOnHost) {
+        // TODO(perf): stream the upload step-major; the whole sequence is uploaded up front for now
+        CB_CHECK_CUDA(c, cudaMemcpyAsync(q->inL, inL, bgrFrame * n, cudaMemcpyHostToDevice, s));
+        CB_CHECK_CUDA(c, cudaMemcpyAsync(q->inR, inR, bgrFrame * n, cudaMemcpyHostToDevice, s));
+    }
+    const int firstId = o->start_id, lastId = o->start_id + n - 1;
+    const int k0 = firstId / R, k1 = lastId / R;  // chunk range
+    const int nChunks = k1 - k0 + 1;
+    if (!peak) {  // static ranges are the same for every frame: upload them once
+        for (size_t j = 0; j < B; ++j) std::memcpy(q->paramsHost + 4 * j, hs.params + 2, 4 * sizeof(int32_t));
+        if ((rc = uploadParams(c, (int)std::min<size_t>(B, (size_t)n), q->paramsHost, s))) return rc;
+    }
+    // a sequence that starts at id 1 starts from the constructor's block initialisation (superpixels.cu:56-58)
+    if (firstId == 1 && (rc = launch_sp_reset(c, 1, slotIota(c), s))) return rc;
+    for (int g0 = 0; g0 < nChunks; g0 += (int)B) {  // groups of at most B chunks (one slot per chunk)
+        const int gN = std::min<int>((int)B, nChunks - g0);
+        for (int st = 0; st < R; ++st) {
+            // chunks of this group that own a frame at this step form a contiguous range [ca, cb)
+            int ca = -1, cb = -1;
+            for (int j = 0; j < gN; ++j) {
+                const int id = (k0 + g0 + j) * R + st;
+                if (id >= firstId && id <= lastId && id >= 1) {
+                    if (ca < 0) ca = j;
+                    cb = j + 1;
+                }
+            }
+            if (ca < 0) continue;
+            const int nb = cb - ca;
+            const int idA = (k0 + g0 + ca) * R + st;
+            const size_t fiA = (size_t)(idA - firstId);            // frame index of the first chunk in the batch
+            const size_t fStride = (size_t)R;                      // frames between consecutive chunks
+            const int* slots = slotIota(c) + ca;
+            const uint8_t* bl = devL + bgrFrame * fiA;
+            const uint8_t* br = devR + bgrFrame * fiA;
+            // disparity
+            int16_t* dB = dispOut ? dispDev + pxFrame * fiA : dispDev;
+            const size_t dStride = dispOut ? pxFrame * 2 * fStride : pxFrame * 2;
+            if ((rc = cartb200_disparity(c, nb, bl, br, W * 3, bgrFrame * fStride, dB, W * 2, dStride, s))) return rc;
+            // derivative + per-frame histogram
+            int16_t* vB = (peak ? q->deriv + pxFrame * 2 * fiA : q->deriv);
+            const size_t vStride = peak ? pxFrame * 4 * fStride : pxFrame * 4;
+            // histograms are stored batch-contiguously in a staging area and scattered on the host
+            if ((rc = launch_derivative(c, nb, ImgBatch<const int16_t>{dB, W * 2, dStride},
+                                        ImgBatch<int16_t>{vB, W * 4, vStride}, q->hist + 512 * (size_t)0, s)))
+                return rc;
+            // histogram rows for this batch land at q->hist[0..nb); move them to their frame slots
+            if (peak) {
+                for (int j = 0; j < nb; ++j)
+                    CB_CHECK_CUDA(c, cudaMemcpyAsync(q->histHost + 512 * (fiA + j * fStride), q->hist + 512 * (size_t)j,
+                                                     512 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            }
+            // superpixels: reset + iteration schedule (superpixels.cu:93-113)
+            const bool resetStep = st == 0;  // id % R == 0
+            if (resetStep && (rc = launch_sp_reset(c, nb, slots, s))) return rc;
+            uint16_t* lB = peak ? q->labels + pxFrame * fiA : q->labels;
+            const size_t lStride = peak ? pxFrame * 2 * fStride : pxFrame * 2;
+            const ImgBatch<const int16_t> dv{vB, W * 4, vStride};
+            // id == 1 also gets the initial iteration count (only chunk 0 at step 1 can be id 1)
+            if (!resetStep && idA == 1) {
+                if ((rc = launch_sp_relax(c, 1, slots, o->sp_initial_iterations, ImgBatch<const uint8_t>{bl, W * 3, bgrFrame * fStride},
+                                          dv, true, ImgBatch<uint16_t>{lB, W * 2, lStride}, s)))
+                    return rc;
+                if (nb > 1 &&
+                    (rc = launch_sp_relax(c, nb - 1, slots + 1, o->sp_iterations,
+                                          ImgBatch<const uint8_t>{bl + bgrFrame * fStride, W * 3, bgrFrame * fStride},
+                                          ImgBatch<const int16_t>{(const int16_t*)((const char*)vB + vStride), W * 4, vStride}, true,
+                                          ImgBatch<uint16_t>{(uint16_t*)((char*)lB + lStride), W * 2, lStride}, s)))
+                    return rc;
+            } else {
+                const int its = resetStep ? o->sp_initial_iterations : o->sp_iterations;
+                if ((rc = launch_sp_relax(c, nb, slots, its, ImgBatch<const uint8_t>{bl, W * 3, bgrFrame * fStride}, dv, true,
+                                          ImgBatch<uint16_t>{lB, W * 2, lStride}, s)))
+                    return rc;
+            }
+            if (!peak) {
+                // static ranges: vote + assign right away
+                if ((rc = launch_sp_planeseg(c, nb, dv, ImgBatch<const uint16_t>{lB, W * 2, lStride}, c->maxLabels,
+                                             c->paramsDev, ImgBatch<uint8_t>{q->unsm, W, pxFrame},
+                                             ImgBatch<uint8_t>{planesDev + pxFrame * fiA, W, pxFrame * fStride}, s)))
+                    return rc;
+            }
+        }
+    }
+    if (peak) {
+        // second phase: parameters in id order, then vote + assign for every frame
+        CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
+        std::vector<int32_t> hv(256);
+        for (int i = 0; i < n; ++i) {
+            const int32_t* h = q->histHost + 512 * (size_t)i;
+            for (int b = 0; b < 256; ++b) hv[b] = h[2 * b];  // channel 0 = vertical (sp_planeseg.cu:358-359)
+            spUpdate(hs, *o, firstId + i, hv.data(), q->paramsHost + 4 * (size_t)i);
+        }
+        for (int b0 = 0; b0 < n; b0 += (int)B) {
+            const int nb = std::min<int>((int)B, n - b0);
+            if ((rc = uploadParams(c, nb, q->paramsHost + 4 * (size_t)b0, s))) return rc;
+            if ((rc = launch_sp_planeseg(c, nb, ImgBatch<const int16_t>{q->deriv + pxFrame * 2 * b0, W * 4, pxFrame * 4},
+                                         ImgBatch<const uint16_t>{q->labels + pxFrame * b0, W * 2, pxFrame * 2}, c->maxLabels,
+                                         c->paramsDev, ImgBatch<uint8_t>{q->unsm, W, pxFrame},
+                                         ImgBatch<uint8_t>{planesDev + pxFrame * b0, W, pxFrame}, s)))
+                return rc;
+        }
+    }
+    if (outputsOnHost) {
+        CB_CHECK_CUDA(c, cudaMemcpyAsync(planesOut, planesDev, pxFrame * n, cudaMemcpyDeviceToHost, s));
+        if (dispOut) CB_CHECK_CUDA(c, cudaMemcpyAsync(dispOut, dispDev, pxFrame * 2 * n, cudaMemcpyDeviceToHost, s));
+    }
+    if (outputsOnHost || inputsOnHost) CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
+    return CARTB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cartb200_run_sequence_host(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const uint8_t* l,
+                               const uint8_t* r, uint8_t* planes, int16_t* disp) {
+    return runSequence(c, o, n, l, r, true, planes, disp, true, nullptr);
+}
+
+int cartb200_run_sequence_device(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const uint8_t* l,
+                                 const uint8_t* r, uint8_t* planes, int16_t* disp, void* stream) {
+    return runSequence(c, o, n, l, r, false, planes, disp, false, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// Shared declarations for the cartb200 CUDA sources (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/cartb200.h"
+
+namespace cb {
+
+constexpr int16_t kInvalid = -32768;  // CARTSLAM_DISPARITY_INVALID
+constexpr int kNumSMs = 148;
+
+template <typename T>
+struct Img {  // pitched device image view
+    T* data;
+    size_t pitch;  // bytes
+    __host__ __device__ __forceinline__ T* row(int y) const { return (T*)((char*)data + (size_t)y * pitch); }
+    __host__ __device__ __forceinline__ T& at(int x, int y) const { return row(y)[x]; }
+};
+
+template <typename T>
+struct ImgBatch {  // n frames with a constant byte stride
+    T* data;
+    size_t pitch, frameStride;  // bytes
+    __host__ __device__ __forceinline__ Img<T> frame(int f) const {
+        return Img<T>{(T*)((char*)data + (size_t)f * frameStride), pitch};
+    }
+};
+
+inline int ceilDiv(int a, int b) { return (a + b - 1) / b; }
+inline size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct PlaneRanges {
+    int hS, hE, vS, vE;
+};
+
+}  // namespace cb
+
+// The context. Owns every scratch buffer, sized at create time for max_batch frames.
+struct cartb200_ctx {
+    cartb200_config cfg;
+    std::string err;
+    long long launches = 0;
+    size_t scratchBytes = 0;
+    int W = 0, H = 0, D = 0, B = 0, P = 0;
+    // SGM scratch
+    uint8_t* grayL = nullptr;   // [B][H][grayPitch]
+    uint8_t* grayR = nullptr;
+    size_t grayPitch = 0;
+    uint32_t* censusL = nullptr;  // [B][H][censusPitch/4]
+    uint32_t* censusR = nullptr;
+    size_t censusPitch = 0;
+    uint8_t* volumes = nullptr;  // [P][B][H][W][D]
+    size_t volFrameStride = 0, volPathStride = 0;
+    uint16_t* wtaL = nullptr;  // [B][H][dispPitch/2]
+    uint16_t* wtaR = nullptr;
+    uint16_t* medL = nullptr;
+    uint16_t* medR = nullptr;
+    size_t dispPitch = 0;
+    // planeseg scratch
+    int32_t* paramsDev = nullptr;  // [B][4]
+    uint32_t* votes = nullptr;     // [B][maxLabels][4]
+    // superpixels
+    int maxLabels = 0, spBlocksPerRow = 0;
+    uint16_t* spLabels = nullptr;  // [B][H][spLabelPitch/2] persistent
+    size_t spLabelPitch = 0;
+    uint8_t* spYcc = nullptr;  // [B][H][W][4] Y,Cr,Cb,border-flag scratch
+    double* spStats = nullptr;     // [B][maxLabels][kStatDoubles]
+    uint16_t* spNew = nullptr;     // [B][H][W] decided labels (0xFFFF = not listed)
+    // sequence runner scratch (lazy)
+    void* seq = nullptr;
+};
+
+#define CB_CHECK_CUDA(ctx, expr)                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                        \
+            return CARTB200_E_CUDA;                                                                  \
+        }                                                                                            \
+    } while (0)
+
+#define CB_LAUNCH_CHECK(ctx)                                                                         \
+    do {                                                                                             \
+        (ctx)->launches++;                                                                           \
+        cudaError_t e__ = cudaPeekAtLastError();                                                     \
+        if (e__ != cudaSuccess) {                                                                    \
+            (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + std::to_string(__LINE__); \
+            return CARTB200_E_CUDA;                                                                  \
+        }                                                                                            \
+    } while (0)
+
+// stage launchers (defined in the per-stage .cu files); all return CARTB200_* codes
+namespace cb {
+int launch_gray_census(cartb200_ctx* c, int n, ImgBatch<const uint8_t> left, ImgBatch<const uint8_t> right, cudaStream_t s);
+int launch_aggregate(cartb200_ctx* c, int n, cudaStream_t s);
+int launch_wta(cartb200_ctx* c, int n, cudaStream_t s);
+int launch_sgm_post(cartb200_ctx* c, int n, ImgBatch<int16_t> disp, cudaStream_t s);
+int launch_interpolate(cartb200_ctx* c, int n, ImgBatch<int16_t> disp, int radius, int iterations, int minD, int maxD, cudaStream_t s);
+int launch_derivative(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<int16_t> deriv, int32_t* hist, cudaStream_t s);
+int launch_naive_derivative(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<int16_t> deriv, int32_t* hist, cudaStream_t s);
+int launch_classify(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, int channels, int channel, const int32_t* paramsDev, ImgBatch<uint8_t> planes, cudaStream_t s);
+int launch_sp_planeseg(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, ImgBatch<const uint16_t> labels, int maxLabel, const int32_t* paramsDev, ImgBatch<uint8_t> unsm, ImgBatch<uint8_t> planes, cudaStream_t s);
+int launch_sp_reset(cartb200_ctx* c, int n, const int* slotsDev, cudaStream_t s);
+int launch_sp_relax(cartb200_ctx* c, int n, const int* slotsDev, int iterations, ImgBatch<const uint8_t> left, ImgBatch<const int16_t> deriv, bool hasDeriv, ImgBatch<uint16_t> out, cudaStream_t s);
+int launch_border_map(cartb200_ctx* c, Img<const uint16_t> labels, Img<uint8_t> border, cudaStream_t s);
+}  // namespace cb

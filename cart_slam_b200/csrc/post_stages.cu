@@ -1,0 +1,310 @@
+// Post-SGM stages: disparity smoothing, directional derivatives + histograms, naive low-pass
+// derivative + histogram, plane classification and the superpixel vote.  Each kernel restates one
+// reference kernel (cited below) on a B200-sized grid: frames are batched in blockIdx.z, tiles are
+// smaller than the reference's 128x128 so a KITTI frame yields hundreds of CTAs instead of 30, the
+// reference's tile-loader semantics come from tile_ref.cuh, histograms are privatised in shared memory
+// and merged with one atomic per non-empty bin.
+#include "common.cuh"
+#include "tile_ref.cuh"
+
+namespace cb {
+
+struct DispAccessor {
+    Img<const int16_t> im;
+    __device__ __forceinline__ int16_t operator()(int x, int y) const { return __ldg(im.row(y) + x); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// interpolateKernel, /root/reference/src/modules/disparity/interpolation.cu:17-82.
+// One CTA per reference 64x64 tile (the tile is the unit of the reference's semantics: halo values
+// stay fixed over the iterations).  Canonical Jacobi schedule: two shared buffers.
+// src and dst are different images (the reference updates in place while neighbouring blocks still
+// read their halos - an inter-block race; canonical = every tile reads the original image).
+__global__ void __launch_bounds__(256) interpolate_kernel(ImgBatch<const int16_t> src, ImgBatch<int16_t> dst, int W,
+                                                          int H, int radius, int iterations, int minD, int maxD) {
+    extern __shared__ int16_t sm[];
+    const int pad = radius - 1, S = 64 + 2 * pad, N = S * S;
+    int16_t* cur = sm;
+    int16_t* nxt = sm + N;
+    const int bx = blockIdx.x, by = blockIdx.y, f = blockIdx.z;
+    TileGeom g{W, H, 64, 64, pad, pad, 4, 4, (long)N};
+    DispAccessor acc{src.frame(f)};
+    TileEval<int16_t, DispAccessor> te(acc, g, bx, by, kInvalid);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const int ly = i / S - pad, lx = i % S - pad;
+        const int16_t v = te.template value<true>(lx, ly);
+        cur[i] = v;
+        nxt[i] = v;
+    }
+    __syncthreads();
+    const unsigned minCount = (unsigned)(radius * radius + 1);
+    for (int it = 0; it < iterations; ++it) {
+        for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+            const int ly = i >> 6, lx = i & 63;
+            if (bx * 64 + lx >= W || by * 64 + ly >= H) continue;
+            int sum = 0;
+            unsigned count = 0;
+            for (int l = -pad; l <= pad; ++l) {
+                const int16_t* rowp = cur + (ly + l + pad) * S + lx + pad;
+                for (int k = -pad; k <= pad; ++k) {
+                    const int v = rowp[k];
+                    if (v > minD && v < maxD) {
+                        sum += v;
+                        count++;
+                    }
+                }
+            }
+            nxt[(ly + pad) * S + lx + pad] = count > minCount ? (int16_t)(sum / (int)count) : kInvalid;
+        }
+        __syncthreads();
+        int16_t* t = cur;
+        cur = nxt;
+        nxt = t;
+        // every in-image tile cell of `nxt` is rewritten by the next pass and the other cells (halo,
+        // out-of-image) are identical in both buffers, so no copy-back is needed
+    }
+    Img<int16_t> out = dst.frame(f);
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+        const int ly = i >> 6, lx = i & 63;
+        const int x = bx * 64 + lx, y = by * 64 + ly;
+        if (x < W && y < H) out.at(x, y) = cur[(ly + pad) * S + lx + pad];
+    }
+}
+
+int launch_interpolate(cartb200_ctx* c, int n, ImgBatch<int16_t> disp, int radius, int iterations, int minD, int maxD,
+                       cudaStream_t s) {
+    if (radius <= 0) return CARTB200_OK;
+    const int pad = radius - 1, S = 64 + 2 * pad;
+    const size_t smem = (size_t)2 * S * S * sizeof(int16_t);
+    if (smem > 200 * 1024) {
+        c->err = "interpolate: smoothing radius too large for shared memory";
+        return CARTB200_E_UNSUPPORTED;
+    }
+    // stage the original image (canonical out-of-place read), medL is free at this point
+    ImgBatch<int16_t> tmp{(int16_t*)c->medL, c->dispPitch, c->dispPitch * (size_t)c->H};
+    for (int f = 0; f < n; ++f) {
+        Img<int16_t> a = disp.frame(f), b = tmp.frame(f);
+        CB_CHECK_CUDA(c, cudaMemcpy2DAsync(b.data, b.pitch, a.data, a.pitch, (size_t)c->W * 2, c->H,
+                                           cudaMemcpyDeviceToDevice, s));
+    }
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(interpolate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    dim3 grid(ceilDiv(c->W, 64), ceilDiv(c->H, 64), n);
+    ImgBatch<const int16_t> src{tmp.data, tmp.pitch, tmp.frameStride};
+    interpolate_kernel<<<grid, 256, smem, s>>>(src, disp, c->W, c->H, radius, iterations, minD, maxD);
+    CB_LAUNCH_CHECK(c);
+    return CARTB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// calculateDirectionalDerivatives + mergeDerivativeHistograms,
+// /root/reference/src/modules/disparity/derivative.cu:27-116.
+// CTA = 128 x 8 pixels of one reference tile row band; thread = one column, 8 rows.
+constexpr int kDerivRows = 8;
+__global__ void __launch_bounds__(128) derivative_kernel(ImgBatch<const int16_t> disp, ImgBatch<int16_t> deriv,
+                                                         int32_t* __restrict__ hist, int W, int H) {
+    __shared__ int sh[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int y0 = blockIdx.y * kDerivRows;
+    if (x < W) {
+        TileGeom g{W, H, 128, 128, 2, 2, 4, 4, 132L * 132L};
+        DispAccessor acc{disp.frame(f)};
+        const int bx = x >> 7, lx = x & 127;
+        Img<int16_t> out = deriv.frame(f);
+        for (int r = 0; r < kDerivRows; ++r) {
+            const int y = y0 + r;
+            if (y >= H) break;
+            const int by = y >> 7, ly = y & 127;
+            TileEval<int16_t, DispAccessor> te(acc, g, bx, by, kInvalid);
+            const int16_t up = te.template value<true>(lx, ly - 2), dn = te.template value<true>(lx, ly + 2);
+            const int16_t lf = te.template value<true>(lx - 2, ly), rt = te.template value<true>(lx + 2, ly);
+            const int16_t dv = (int16_t)(dn - up), dh = (int16_t)(rt - lf);
+            const bool vv = up != kInvalid && dn != kInvalid, hv = lf != kInvalid && rt != kInvalid;
+            short2 o;
+            o.x = vv ? dv : kInvalid;
+            o.y = hv ? dh : kInvalid;
+            *reinterpret_cast<short2*>(out.row(y) + 2 * x) = o;
+            if (vv && dv >= -128 && dv <= 127) atomicAdd(&sh[2 * (dv + 128)], 1);
+            if (hv && dh >= -128 && dh <= 127) atomicAdd(&sh[2 * (dh + 128) + 1], 1);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 512; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[(size_t)f * 512 + i], sh[i]);
+}
+
+int launch_derivative(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<int16_t> deriv, int32_t* hist,
+                      cudaStream_t s) {
+    CB_CHECK_CUDA(c, cudaMemsetAsync(hist, 0, (size_t)n * 512 * sizeof(int32_t), s));
+    dim3 grid(ceilDiv(c->W, 128), ceilDiv(c->H, kDerivRows), n);
+    derivative_kernel<<<grid, 128, 0, s>>>(disp, deriv, hist, c->W, c->H);
+    CB_LAUNCH_CHECK(c);
+    return CARTB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// calculateDerivatives (naive), /root/reference/src/modules/planeseg/planeseg.cu:31-142.
+// CTA = one 128-column reference tile x a band of kNaiveRows local rows.  Raw rows (with the
+// reference's halo semantics) are staged in shared memory, the 5-tap valid-mean is out-of-place
+// (canonical schedule), halo rows stay unfiltered (Q10b).
+constexpr int kNaiveRows = 16;
+__global__ void __launch_bounds__(128) naive_derivative_kernel(ImgBatch<const int16_t> disp, ImgBatch<int16_t> deriv,
+                                                               int32_t* __restrict__ hist, int W, int H) {
+    __shared__ int sh[256];
+    __shared__ int16_t raw[kNaiveRows + 6][128];  // local rows r0-3 .. r0+kNaiveRows+2
+    __shared__ int16_t fil[kNaiveRows + 2][128];  // F rows r0-1 .. r0+kNaiveRows
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+    const int f = blockIdx.z, bx = blockIdx.x;
+    const int bandsPerTile = 128 / kNaiveRows;
+    const int by = blockIdx.y / bandsPerTile, r0 = (blockIdx.y % bandsPerTile) * kNaiveRows;
+    const int lx = threadIdx.x, x = bx * 128 + lx;
+    TileGeom g{W, H, 128, 128, 0, 2, 4, 4, 128L * 144L};
+    DispAccessor acc{disp.frame(f)};
+    TileEval<int16_t, DispAccessor> te(acc, g, bx, by, kInvalid);
+    for (int k = 0; k < kNaiveRows + 6; ++k) {
+        const int ly = r0 - 3 + k;
+        raw[k][lx] = (ly >= -2 && ly < 130) ? te.template value<true>(lx, ly) : kInvalid;
+    }
+    // each thread only touches its own column: no barrier needed between the phases
+    for (int k = 0; k < kNaiveRows + 2; ++k) {
+        const int ly = r0 - 1 + k;  // local row of F
+        int16_t v;
+        if (ly < 0 || ly >= 128) {
+            v = raw[k + 2][lx];  // unfiltered halo row
+        } else {
+            int16_t sum = 0;
+            int count = 0;
+#pragma unroll
+            for (int t = 0; t < 5; ++t) {
+                const int16_t d = raw[k + t][lx];
+                if (d != kInvalid) {
+                    sum = (int16_t)(sum + d);
+                    count++;
+                }
+            }
+            v = count == 0 ? kInvalid : (int16_t)(sum / count);
+        }
+        fil[k][lx] = v;
+    }
+    __syncthreads();  // histogram zeroing visible
+    if (x < W) {
+        Img<int16_t> out = deriv.frame(f);
+        for (int k = 0; k < kNaiveRows; ++k) {
+            const int y = by * 128 + r0 + k;
+            if (y >= H) break;
+            const int16_t p = fil[k][lx], cval = fil[k + 1][lx], nx = fil[k + 2][lx];
+            const int16_t dv = (int16_t)(nx - p);
+            const bool valid = cval != kInvalid && nx != kInvalid && p != kInvalid;
+            out.at(x, y) = valid ? dv : kInvalid;
+            if (valid && dv >= -128 && dv <= 127) atomicAdd(&sh[dv + 128], 1);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[(size_t)f * 256 + i], sh[i]);
+}
+
+int launch_naive_derivative(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<int16_t> deriv,
+                            int32_t* hist, cudaStream_t s) {
+    CB_CHECK_CUDA(c, cudaMemsetAsync(hist, 0, (size_t)n * 256 * sizeof(int32_t), s));
+    const int tilesY = ceilDiv(c->H, 128);
+    dim3 grid(ceilDiv(c->W, 128), tilesY * (128 / kNaiveRows), n);
+    naive_derivative_kernel<<<grid, 128, 0, s>>>(disp, deriv, hist, c->W, c->H);
+    CB_LAUNCH_CHECK(c);
+    return CARTB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// classifyPlanes (naive) range rule, /root/reference/src/modules/planeseg/planeseg.cu:188-197.
+__device__ __forceinline__ uint8_t classify_one(int16_t d, int hS, int hE, int vS, int vE) {
+    if (d != kInvalid && d >= hS && d < hE) return CARTB200_PLANE_HORIZONTAL;
+    if (d != kInvalid && d >= vS && d < vE) return CARTB200_PLANE_VERTICAL;
+    return CARTB200_PLANE_UNKNOWN;
+}
+
+__global__ void __launch_bounds__(256) classify_kernel(ImgBatch<const int16_t> deriv, int channels, int channel,
+                                                       const int32_t* __restrict__ params, ImgBatch<uint8_t> planes,
+                                                       int W, int H) {
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int hS = params[4 * f], hE = params[4 * f + 1], vS = params[4 * f + 2], vE = params[4 * f + 3];
+    const int16_t d = __ldg(deriv.frame(f).row(y) + (size_t)x * channels + channel);
+    planes.frame(f).at(x, y) = classify_one(d, hS, hE, vS, vE);
+}
+
+int launch_classify(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, int channels, int channel,
+                    const int32_t* paramsDev, ImgBatch<uint8_t> planes, cudaStream_t s) {
+    dim3 grid(ceilDiv(c->W, 256), c->H, n);
+    classify_kernel<<<grid, 256, 0, s>>>(deriv, channels, channel, paramsDev, planes, c->W, c->H);
+    CB_LAUNCH_CHECK(c);
+    return CARTB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// performSuperPixelClassifications + classifyPlanes (SP),
+// /root/reference/src/modules/planeseg/sp_planeseg.cu:25-184 (previousPlanesCount == 0).
+// Votes are 32-bit global counters [frame][label][4]; lanes of a warp that hit the same
+// (label, plane) counter are merged with __match_any_sync before the atomic.
+__global__ void __launch_bounds__(256) sp_vote_kernel(ImgBatch<const int16_t> deriv, ImgBatch<const uint16_t> labels,
+                                                      int maxLabel, const int32_t* __restrict__ params,
+                                                      ImgBatch<uint8_t> unsm, uint32_t* __restrict__ votes,
+                                                      int voteStride, int W, int H) {
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const bool in = x < W;
+    unsigned key = 0xFFFFFFFFu;
+    if (in) {
+        const int hS = params[4 * f], hE = params[4 * f + 1], vS = params[4 * f + 2], vE = params[4 * f + 3];
+        const int16_t d = __ldg(deriv.frame(f).row(y) + 2 * (size_t)x);
+        const uint8_t p = classify_one(d, hS, hE, vS, vE);
+        unsm.frame(f).at(x, y) = p;
+        const unsigned l = __ldg(labels.frame(f).row(y) + x);
+        if ((int)l < maxLabel) key = l * 4 + p;
+    }
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, key);
+    if (key != 0xFFFFFFFFu && (threadIdx.x & 31) == (__ffs(peers) - 1))
+        atomicAdd(&votes[(size_t)f * voteStride + key], (unsigned)__popc(peers));
+}
+
+__global__ void __launch_bounds__(256) sp_assign_kernel(ImgBatch<const uint16_t> labels, int maxLabel,
+                                                        const uint32_t* __restrict__ votes, int voteStride,
+                                                        ImgBatch<uint8_t> planes, int W, int H) {
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const unsigned l = __ldg(labels.frame(f).row(y) + x);
+    uint8_t best = CARTB200_PLANE_UNKNOWN;
+    if ((int)l < maxLabel) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(votes + (size_t)f * voteStride + 4 * l));
+        int maxVotes = (int)v.z;  // UNKNOWN
+        if ((int)v.y > maxVotes) {
+            maxVotes = (int)v.y;
+            best = CARTB200_PLANE_VERTICAL;
+        }
+        if ((int)v.x > maxVotes) best = CARTB200_PLANE_HORIZONTAL;
+    }
+    planes.frame(f).at(x, y) = best;
+}
+
+int launch_sp_planeseg(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, ImgBatch<const uint16_t> labels,
+                       int maxLabel, const int32_t* paramsDev, ImgBatch<uint8_t> unsm, ImgBatch<uint8_t> planes,
+                       cudaStream_t s) {
+    const int voteStride = c->maxLabels * 4;
+    CB_CHECK_CUDA(c, cudaMemsetAsync(c->votes, 0, (size_t)n * voteStride * sizeof(uint32_t), s));
+    dim3 grid(ceilDiv(c->W, 256), c->H, n);
+    sp_vote_kernel<<<grid, 256, 0, s>>>(deriv, labels, maxLabel, paramsDev, unsm, c->votes, voteStride, c->W, c->H);
+    CB_LAUNCH_CHECK(c);
+    sp_assign_kernel<<<grid, 256, 0, s>>>(labels, maxLabel, c->votes, voteStride, planes, c->W, c->H);
+    CB_LAUNCH_CHECK(c);
+    return CARTB200_OK;
+}
+
+}  // namespace cb

@@ -65,7 +65,8 @@ def ground_truth_disparity(W: int, H: int, D: int, min_disp: int, seed: int, fra
     h0 = int(0.45 * H)
     y = np.arange(H, dtype=np.int64)[:, None]
     x = np.arange(W, dtype=np.int64)[None, :]
-    road = min_disp + (y - h0) * (D - 16) // max(1, H - h0)
+    span = min(D - 16, (45 * max(1, H - h0)) // 100)  # at most 0.45 px of disparity per row
+    road = min_disp + (y - h0) * span // max(1, H - h0)
     slabs = min_disp + 8 + 16 * ((x // 160) % 4)
     d = np.where(y >= h0, np.broadcast_to(road, (H, W)), np.broadcast_to(slabs, (H, W))).astype(np.int64)
     # 6 constant-disparity boxes, re-seeded every 10 frames

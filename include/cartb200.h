@@ -1,0 +1,212 @@
+/* cartb200 - C ABI of the B200-native dense stereo front end (disparity -> plane segmentation).
+ *
+ * This is the drop-in boundary for CART-SLAM's module layer: every entry point replaces the device work
+ * of one reference module (or one third-party call inside it) and is what a reference-side FFI for the
+ * path would bind.  Plain pointers and sizes only; no C++ / torch types.
+ *
+ * Conventions
+ *  - All image pointers are DEVICE pointers unless the name ends in `_host`.  Pitches are in BYTES.
+ *  - Every call is asynchronous on the caller-supplied `stream` (a cudaStream_t passed as void*; NULL =
+ *    the legacy default stream), except the `_host` convenience calls, which synchronise before returning.
+ *  - Batch calls take `n` frames laid out with a constant byte stride between frames.
+ *  - Return value: 0 on success, < 0 = CARTB200_E_*.  Nothing throws, nothing calls exit().
+ *    cartb200_last_error(ctx) returns a description of the last failure on that context.
+ *  - A context is not thread-safe; use one context per in-flight frame slot (the reference runs up to
+ *    12 frames concurrently, /root/reference/include/cartslam.hpp:3-5).
+ */
+#ifndef CARTB200_H
+#define CARTB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CARTB200_OK 0
+#define CARTB200_E_ARG (-1)
+#define CARTB200_E_SHAPE (-2)
+#define CARTB200_E_CUDA (-3)
+#define CARTB200_E_NOMEM (-4)
+#define CARTB200_E_UNSUPPORTED (-5)
+
+#define CARTB200_DISPARITY_INVALID (-32768) /* /root/reference/include/modules/disparity.hpp:17 */
+#define CARTB200_PLANE_HORIZONTAL 0         /* /root/reference/include/modules/planeseg.hpp:37-41 */
+#define CARTB200_PLANE_VERTICAL 1
+#define CARTB200_PLANE_UNKNOWN 2
+
+typedef struct cartb200_ctx cartb200_ctx;
+
+/* Mirrors the constructor arguments of the reference modules on the path.
+ * disparity:   ImageDisparityModule(imageRes, minDisparity, numDisparities, blockSize, smoothingRadius,
+ *              smoothingIterations)  /root/reference/include/modules/disparity.hpp:26-34, JSON defaults
+ *              /root/reference/src/cartconfig.cpp:144-152.  p1/p2/uniqueness_ratio/paths are the values
+ *              the reference gets implicitly from cv::cuda::createStereoSGM (10, 120, 12, 4 = MODE_HH4).
+ * superpixels: SuperPixelModule(...) /root/reference/include/modules/superpixels.hpp:17-28, JSON defaults
+ *              /root/reference/src/cartconfig.cpp:121-134. */
+typedef struct cartb200_config {
+    int width, height;
+    int max_batch; /* frames per batched call (scratch is sized for this) */
+    /* disparity */
+    int min_disparity;    /* 4 */
+    int num_disparities;  /* 64, 128 or 256 */
+    int p1, p2;           /* 10, 120 */
+    int uniqueness_ratio; /* 12 */
+    int paths;            /* 4 (MODE_HH4) or 8 (MODE_HH) */
+    int smoothing_radius; /* <= 0: no interpolation */
+    int smoothing_iterations;
+    /* superpixels (enable_superpixels = 0 skips allocating their scratch) */
+    int enable_superpixels;
+    int sp_block_size; /* 12 */
+    double sp_direct_clique_cost, sp_diagonal_clique_cost;
+    double sp_compactness_weight, sp_progressive_compactness_cost, sp_image_weight, sp_disparity_weight;
+} cartb200_config;
+
+/* Fills `cfg` with the reference's JSON defaults (cartconfig.cpp:121-152) for a WxH stream. */
+void cartb200_default_config(cartb200_config* cfg, int width, int height);
+
+int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out);
+void cartb200_destroy(cartb200_ctx* ctx);
+const char* cartb200_last_error(const cartb200_ctx* ctx);
+const char* cartb200_version(void);
+/* Number of kernels this context has launched so far (bench.py's `gpu_launches`). */
+long long cartb200_launch_count(const cartb200_ctx* ctx);
+/* Bytes of device scratch the context owns. */
+size_t cartb200_scratch_bytes(const cartb200_ctx* ctx);
+
+/* ---- disparity stage ------------------------------------------------------------------------------
+ * Replaces ImageDisparityModule::runInternal's device work
+ * (/root/reference/src/modules/disparity/disparity.cu:49-80): cvtColor BGR2GRAY x2 (:66-67),
+ * cv::cuda::StereoSGM::compute (:71, third party) and disparity::interpolate (:73-75,
+ * /root/reference/src/modules/disparity/interpolation.cu:85-99).
+ * left/right: n frames of CV_8UC3 BGR.  disparity: n frames of CV_16SC1 (x16 fixed point). */
+int cartb200_disparity(cartb200_ctx* ctx, int n, const uint8_t* left_bgr, const uint8_t* right_bgr, size_t bgr_pitch,
+                       size_t bgr_frame_stride, int16_t* disparity, size_t disp_pitch, size_t disp_frame_stride,
+                       void* stream);
+
+/* The three sub-stages of cartb200_disparity, exposed for parity tests and profiling.
+ * gray_census: BGR -> gray (kept inside the context for the L/R-check mask) + 9x7 census, both images.
+ * aggregate:   P path volumes (u8 [n][y][x][d]) inside the context.
+ * wta_post:    WTA + uniqueness + sub-pixel, right disparity, 3x3 medians, L/R check, range correction,
+ *              then (smoothing_radius > 0) the interpolation pass. */
+int cartb200_sgm_gray_census(cartb200_ctx* ctx, int n, const uint8_t* left_bgr, const uint8_t* right_bgr,
+                             size_t bgr_pitch, size_t bgr_frame_stride, void* stream);
+int cartb200_sgm_aggregate(cartb200_ctx* ctx, int n, void* stream);
+int cartb200_sgm_wta_post(cartb200_ctx* ctx, int n, int16_t* disparity, size_t disp_pitch, size_t disp_frame_stride,
+                          void* stream);
+/* In-place smoothing of an existing CV_16SC1 image (interpolation.cu:85-99). min_disparity is the
+ * already-scaled lower bound (module passes minDisparity*16), max_disparity the upper bound (module passes
+ * the image width, unscaled - reproduced as is). */
+int cartb200_interpolate(cartb200_ctx* ctx, int n, int16_t* disparity, size_t disp_pitch, size_t disp_frame_stride,
+                         int radius, int iterations, int min_disparity, int max_disparity, void* stream);
+
+/* Debug/parity access to the context's intermediates of the last SGM call (device pointers, tightly
+ * packed with the returned pitches).  which: 0 census L (u32), 1 census R (u32), 2 gray L (u8),
+ * 3 left raw WTA (u16), 4 right raw WTA (u16), 10+p aggregated volume of path p (u8 [n][H][W][D]). */
+int cartb200_sgm_intermediate(cartb200_ctx* ctx, int which, const void** ptr, size_t* pitch, size_t* frame_stride);
+
+/* ---- derivative stage ----------------------------------------------------------------------------
+ * Replaces ImageDisparityDerivativeModule::runInternal
+ * (/root/reference/src/modules/disparity/derivative.cu:151-184: calculateDirectionalDerivatives :27-97 +
+ * mergeDerivativeHistograms :99-116).  derivative: CV_16SC2 (ch0 vertical, ch1 horizontal);
+ * histogram: n x 256 x 2 int32 (bin = value + 128; ch0 vertical) - "disparity_derivative_histogram". */
+int cartb200_derivative(cartb200_ctx* ctx, int n, const int16_t* disparity, size_t disp_pitch,
+                        size_t disp_frame_stride, int16_t* derivative, size_t deriv_pitch, size_t deriv_frame_stride,
+                        int32_t* histogram, void* stream);
+
+/* ---- naive plane segmentation --------------------------------------------------------------------
+ * Replaces DisparityPlaneSegmentationModule::runInternal's kernels
+ * (/root/reference/src/modules/planeseg/planeseg.cu: calculateDerivatives :31-142, mergeHistogram :144-158,
+ * classifyPlanes :160-243 without the temporal vote).
+ * naive_derivative: derivative CV_16SC1 + this frame's 256-bin histogram (n x 256 int32); the running
+ * total across frames is host state (the module layer adds frames in id order).
+ * classify: range rule on channel `channel` of a derivative image with `channels` int16 per pixel. */
+int cartb200_naive_derivative(cartb200_ctx* ctx, int n, const int16_t* disparity, size_t disp_pitch,
+                              size_t disp_frame_stride, int16_t* derivative, size_t deriv_pitch,
+                              size_t deriv_frame_stride, int32_t* histogram, void* stream);
+/* params: n x 4 int32 on the HOST: {horizontalStart, horizontalEnd, verticalStart, verticalEnd} per frame
+ * (PlaneParameters is passed by value to the reference kernels, planeseg.cu:349-350). */
+int cartb200_classify(cartb200_ctx* ctx, int n, const int16_t* derivative, size_t deriv_pitch,
+                      size_t deriv_frame_stride, int channels, int channel, const int32_t* params_host, uint8_t* planes,
+                      size_t planes_pitch, size_t planes_frame_stride, void* stream);
+
+/* ---- superpixels ---------------------------------------------------------------------------------
+ * Replaces SuperPixelModule::runInternal (/root/reference/src/modules/superpixels.cu:71-121) and
+ * ContourRelaxation::relax (/root/reference/src/modules/superpixels/contourrelaxation/contourrelaxation.cu:349-447).
+ * The context owns `max_batch` persistent label images ("slots", one per independent sequence chunk).
+ * reset: createBlockInitialization (initialization.cu:39-59) on the given slots; *max_label_out (host)
+ *        receives the label COUNT ("superpixels_max_label").
+ * relax: for slot s (0..n-1): BGR->YCrCb of left image s, statistics init, `iterations` relaxation
+ *        iterations against derivative image s (CV_16SC2; may be NULL when the disparity weight is <= 0),
+ *        then copies the slot's labels to labels_out (CV_16UC1). slot_ids (host, n ints) selects slots;
+ *        NULL = 0..n-1. */
+int cartb200_superpixels_reset(cartb200_ctx* ctx, int n, const int* slot_ids_host, int* max_label_out, void* stream);
+int cartb200_superpixels_relax(cartb200_ctx* ctx, int n, const int* slot_ids_host, int iterations,
+                               const uint8_t* left_bgr, size_t bgr_pitch, size_t bgr_frame_stride,
+                               const int16_t* derivative, size_t deriv_pitch, size_t deriv_frame_stride,
+                               uint16_t* labels_out, size_t labels_pitch, size_t labels_frame_stride, void* stream);
+/* Overwrite / read a slot's persistent label image (ContourRelaxation::setLabelImage, contourrelaxation.cu:335-338). */
+int cartb200_superpixels_set_labels(cartb200_ctx* ctx, int slot, const uint16_t* labels, size_t labels_pitch,
+                                    void* stream);
+/* Border membership map of findBorderPixels (contourrelaxation.cu:146-219) for parity tests: border u8. */
+int cartb200_superpixels_border_map(cartb200_ctx* ctx, const uint16_t* labels, size_t labels_pitch, uint8_t* border,
+                                    size_t border_pitch, void* stream);
+
+/* ---- superpixel plane segmentation ---------------------------------------------------------------
+ * Replaces SuperPixelDisparityPlaneSegmentationModule::runInternal's kernels
+ * (/root/reference/src/modules/planeseg/sp_planeseg.cu: performSuperPixelClassifications :25-134 and
+ * classifyPlanes :136-184, no temporal vote).  planes_unsmoothed = per-pixel class from the vertical
+ * derivative; planes = per-superpixel majority.  max_label = label COUNT.
+ * Fails with CARTB200_E_UNSUPPORTED when (max_label+1)*6 > 32768 like the reference (:327-331). */
+int cartb200_sp_planeseg(cartb200_ctx* ctx, int n, const int16_t* derivative, size_t deriv_pitch,
+                         size_t deriv_frame_stride, const uint16_t* labels, size_t labels_pitch,
+                         size_t labels_frame_stride, int max_label, const int32_t* params_host,
+                         uint8_t* planes_unsmoothed, uint8_t* planes, size_t planes_pitch, size_t planes_frame_stride,
+                         void* stream);
+
+/* ---- host-side parameter estimation --------------------------------------------------------------
+ * HistogramPeakPlaneParameterProvider::updatePlaneParameters (/root/reference/src/modules/planeseg/planeseg.cu:405-458)
+ * + util::findPeaks (/root/reference/src/utils/peaks.cpp:12-72).  hist256: HOST 256 x int32.
+ * params: HOST {horizontalCenter, verticalCenter, hStart, hEnd, vStart, vEnd}, updated in place.
+ * Returns 1 if the ranges were updated, 0 if the reference's early returns fired, < 0 on error. */
+int cartb200_histogram_peak_update(const int32_t* hist256_host, int32_t* params_host);
+
+/* ---- whole-path convenience with HOST buffers (the end-to-end call timed by bench.py `e2e`) -------
+ * Runs disparity -> derivative -> [superpixels] -> planeseg for n_frames consecutive frames of ONE
+ * sequence given in pinned or pageable host memory, reproducing the reference's per-sequence state
+ * (superpixel reset schedule, running histograms, parameter update cadence; frame ids start_id..).
+ * pipeline: 0 = naive (config/modules/kitti-naive-segmentation.json: disparity -> disparity_planeseg),
+ *           1 = superpixel (config/modules/kitti-planeseg.json minus optflow/depth/vis/temporal smoothing).
+ * provider: 0 = static (static_params = {hS,hE,vS,vE}), 1 = histogram_peak.
+ * Outputs (host, tightly packed): planes n x H x W u8; optional (may be NULL) disparity n x H x W s16.
+ * Host<->device copies are issued inside this call, overlapped with compute. */
+typedef struct cartb200_sequence_opts {
+    int pipeline;
+    int provider;
+    int static_params[4];
+    int update_interval;   /* 30 */
+    int reset_interval;    /* 10 */
+    int sp_initial_iterations, sp_iterations, sp_reset_iterations; /* 18, 6, 64 */
+    int start_id;          /* 1 */
+} cartb200_sequence_opts;
+void cartb200_default_sequence_opts(cartb200_sequence_opts* o);
+int cartb200_run_sequence_host(cartb200_ctx* ctx, const cartb200_sequence_opts* opts, int n_frames,
+                               const uint8_t* left_bgr_host, const uint8_t* right_bgr_host, uint8_t* planes_host,
+                               int16_t* disparity_host);
+/* Same pipeline with inputs already resident on the device (bench.py `value`): device buffers tightly
+ * packed; planes_dev n x H x W u8. */
+int cartb200_run_sequence_device(cartb200_ctx* ctx, const cartb200_sequence_opts* opts, int n_frames,
+                                 const uint8_t* left_bgr_dev, const uint8_t* right_bgr_dev, uint8_t* planes_dev,
+                                 int16_t* disparity_dev, void* stream);
+
+/* CPU evaluation of the closed-form reference-tile mapping used by the kernels (no GPU needed); lets the
+ * CPU test-suite check it against the oracle's literal copyToShared simulation.  Returns the value the
+ * reference's shared tile holds at local (lx, ly) of block (bx, by) for an int32 image. */
+int32_t cartb200_debug_ref_tile_i32(const int32_t* img_host, int W, int H, int bx, int by, int bdx, int bdy, int XB,
+                                    int YB, int y_pad, int x_pad, int interp, long alloc_elems, int32_t undef, int lx,
+                                    int ly);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARTB200_H */
