@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py - stereo frames/s (1242x375, 128 disparities) through disparity -> planeseg on B200.
+
+A "step" is one pass of the hot path over one KITTI-shaped synthetic stereo sequence (BASELINE.json
+configs[1]: 1000 frames, full disparity + superpixels + planeseg on one B200).  With N GPUs every rank
+processes its own sequence (frames shard naturally; the only collective is the final result gather),
+so scaling is "weak".
+
+  value  : frames/s with the sequence already resident in HBM (cartb200_run_sequence_device)
+  e2e    : frames/s through the C ABI call that takes HOST buffers (cartb200_run_sequence_host):
+           pinned host -> device copies of both images and the device -> host copy of the plane labels
+           are inside the timed region
+  roofline    : the path-aggregation kernel (dominant), algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline: OpenCV CPU StereoSGBM (MODE_HH4, all host threads) + the scalar oracle for the planeseg
+                half, on a bounded sample of the same frames
+
+`--impl reference` times that CPU arm alone (the reference has no CPU implementation of the path and
+its GPU path needs OpenCV-CUDA, which cannot be built here - DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, D, MIN_DISP = 1242, 375, 128, 4
+METRIC = "stereo frames/s (1242x375, 128 disp) disparity->planeseg"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_frames(n_frames: int, sequence_id: int):
+    """Synthetic KITTI-shaped sequence (cached under /tmp so both bench arms reuse it)."""
+    from cart_slam_b200.synth import SyntheticSequence
+
+    cache = f"/tmp/cartb200_synth_{W}x{H}_{D}_{n_frames}_{sequence_id}.npz"
+    if os.path.exists(cache):
+        try:
+            z = np.load(cache)
+            return z["L"], z["R"]
+        except Exception:
+            pass
+    seq = SyntheticSequence(W, H, D, min_disp=MIN_DISP, sequence_id=sequence_id, n_frames=n_frames, tint=True)
+    L = np.empty((n_frames, H, W, 3), np.uint8)
+    R = np.empty((n_frames, H, W, 3), np.uint8)
+    for i in range(n_frames):
+        L[i], R[i], _ = seq.frame(i + 1)
+    try:
+        np.savez(cache, L=L, R=R)
+    except Exception:
+        pass
+    return L, R
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm(n_sample: int, L, R):
+    """OpenCV CPU StereoSGBM (all threads) + scalar oracle planeseg half, frames in id order."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+
+    po.lib()
+    try:
+        import cv2
+
+        cv2.setNumThreads(0)
+        sg = cv2.StereoSGBM_create(minDisparity=MIN_DISP, numDisparities=D, blockSize=3, P1=10, P2=120,
+                                   uniquenessRatio=12, mode=cv2.STEREO_SGBM_MODE_HH4)
+        threads = cv2.getNumThreads()
+        sgm_name = f"cv2 {cv2.__version__} StereoSGBM MODE_HH4 ({threads} threads)"
+    except Exception:
+        cv2, sg, threads, sgm_name = None, None, 1, "oracle scalar SGM (cv2 unavailable)"
+    labels, nlab = po.block_init(W, H, 12, 12)
+    t0 = time.perf_counter()
+    for i in range(n_sample):
+        l, r = L[i], R[i]
+        if sg is not None:
+            d = sg.compute(cv2.cvtColor(l, cv2.COLOR_BGR2GRAY), cv2.cvtColor(r, cv2.COLOR_BGR2GRAY))
+            d = np.where(d < MIN_DISP * 16, (MIN_DISP - 1) * 16, d).astype(np.int16)
+        else:
+            d = po.sgm_compute(l, r, D, MIN_DISP)
+        d = po.interpolate(d, 2, 1, MIN_DISP * 16, W)
+        deriv, hist = po.derivative(d)
+        labels, _, _ = po.sp_relax(labels, nlab, po.ycrcb(l), deriv, 24 if i == 0 else 8)
+        po.sp_planeseg(deriv, labels, nlab, 1, 30, -3, 1)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, threads, f"{n_sample} frames of the same sequence: {sgm_name} + scalar oracle interpolate/derivative/superpixels(24 then 8 it.)/sp_planeseg (1 thread)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cartb200", choices=["cartb200", "reference"])
+    ap.add_argument("--frames", type=int, default=1000, help="frames per sequence (BASELINE.json configs[1]: 1000)")
+    ap.add_argument("--batch", type=int, default=16, help="frames (sequence chunks) per batched launch")
+    ap.add_argument("--pipeline", type=int, default=1, help="1 = superpixel pipeline (headline), 0 = naive")
+    ap.add_argument("--cpu-sample", type=int, default=6)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg_workload = {
+        "workload": f"KITTI-shaped synthetic {args.frames}-frame stereo sequence per GPU, {W}x{H}, {D} disparities, "
+                    f"min_disparity {MIN_DISP}, 4 paths (MODE_HH4), smoothing r=2 it=1, "
+                    + ("superpixels 24/8 iterations block 12 reset 64 + superpixel planeseg (kitti-planeseg.json minus optflow/depth/vis/temporal), histogram_peak provider"
+                       if args.pipeline == 1 else "naive planeseg (kitti-naive-segmentation.json), histogram_peak provider"),
+        "frames_per_gpu": args.frames, "batch": args.batch, "pipeline": "superpixel" if args.pipeline == 1 else "naive",
+        "l2": "inputs and intermediates per step (>= 2.8 GB images, 3.8 GB cost volumes per batch) exceed the 126 MB L2",
+    }
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        L, R = make_frames(max(args.cpu_sample, 8), 0)
+        vals = []
+        for it in range(args.warmup + args.steps):
+            v, threads, sample = cpu_arm(args.cpu_sample, L, R)
+            if it >= args.warmup:
+                vals.append(v)
+            if it >= 1 and args.warmup + args.steps > 2 and (it + 1) * args.cpu_sample / max(v, 1e-9) > 240:
+                vals = vals or [v]
+                break
+        v = float(np.mean(vals))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 0, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * args.cpu_sample / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16/s16 integer + f64 superpixel costs",
+            "data": "synthetic", "config": cfg_workload,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    import cart_slam_b200 as cb
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    hbm_peak, peak_src = load_peaks()
+
+    n = args.frames
+    L, R = make_frames(n, rank)
+    hostL = torch.from_numpy(L).pin_memory()
+    hostR = torch.from_numpy(R).pin_memory()
+    devL, devR = hostL.cuda(non_blocking=True), hostR.cuda(non_blocking=True)
+    planes_dev = torch.empty((n, H, W), dtype=torch.uint8, device="cuda")
+    planes_host = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+
+    cfg = cb.Config(W, H, max_batch=args.batch, num_disparities=D, min_disparity=MIN_DISP, smoothing_radius=2,
+                    smoothing_iterations=1, enable_superpixels=args.pipeline == 1, sp_block_size=12)
+    ctx = cb.Context(cfg)
+    opts = cb.SequenceOptions(pipeline=args.pipeline, provider=1, sp_initial_iterations=24, sp_iterations=8,
+                              sp_reset_iterations=64)
+    gather_buf = None
+    if world > 1 and rank == 0:
+        gather_buf = [torch.empty_like(planes_dev) for _ in range(world)]
+
+    def step_device():
+        ctx.run_sequence_device(opts, devL, devR, planes_out=planes_dev)
+        if world > 1:  # the only collective of the path: the final result gather
+            dist.gather(planes_dev, gather_buf, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the host-buffer C ABI call
+    for _ in range(1):
+        ctx.run_sequence_host(opts, hostL, hostR, planes_out=planes_host)
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        ctx.run_sequence_host(opts, hostL, hostR, planes_out=planes_host)
+    e3.record()
+    barrier()
+    ms_e2e = max(e2.elapsed_time(e3), 0.0)
+    wall_e2e = (time.perf_counter() - t0) * 1000.0
+    ms_e2e = max(ms_e2e, wall_e2e)  # the call synchronises internally; take the larger clock
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # roofline of the dominant kernel: one path-aggregation kernel over a batch of `batch` frames
+    roof = None
+    if rank == 0:
+        nb = args.batch
+        ctx.sgm_gray_census(devL[:nb], devR[:nb])
+        for _ in range(3):
+            ctx.sgm_aggregate(nb)
+        torch.cuda.synchronize()
+        reps = 10
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            ctx.sgm_aggregate(nb)
+        a1.record()
+        torch.cuda.synchronize()
+        per_kernel_ms = a0.elapsed_time(a1) / reps / 4  # 4 path kernels per call
+        alg_bytes = nb * (2 * 4 * W * H + W * H * D)   # read both census images, write one u8 volume
+        achieved = alg_bytes / (per_kernel_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "aggregate_path_kernel (mean of the 4 MODE_HH4 path launches)",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "launch_ms": per_kernel_ms,
+                "algorithmic_bytes_per_launch": alg_bytes}
+
+    cpu = None
+    if rank == 0 and world == 1:
+        v, threads, sample = cpu_arm(args.cpu_sample, L, R)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        total_frames = n * args.steps * world
+        out = {
+            "metric": METRIC, "value": total_frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/u16/s16 integer + f64 superpixel costs", "data": "synthetic",
+            "config": cfg_workload,
+            "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(2 * n * H * W * 3), "d2h_bytes_per_step": int(n * H * W)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "library": cb.version(), "scratch_bytes": ctx.scratch_bytes(),
+        }
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

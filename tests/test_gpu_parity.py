@@ -1,0 +1,273 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, on a real GPU.
+Integer stages: bit-exact.  Superpixel labels: >= 99.9 % per-pixel agreement (fp64 costs, CUDA log vs libm)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+import cart_slam_b200 as cb
+import pyoracle as po
+import ref_pipeline as rp
+from cart_slam_b200.synth import SyntheticSequence
+
+LABEL_AGREEMENT = 0.999  # tolerance stated by BASELINE.json north_star
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch.device("cuda:0")
+
+
+SGM_CASES = [
+    # W, H, D, min_disp, paths, n
+    (200, 60, 64, 4, 4, 2),
+    (333, 77, 128, 4, 4, 1),     # ragged sizes
+    (160, 48, 64, 0, 8, 2),      # 8 paths, min_disp 0
+    (300, 50, 256, 7, 4, 1),     # D = 256, odd min_disp
+    (131, 37, 128, 4, 8, 1),     # image narrower than D + margins
+]
+
+
+@pytest.mark.parametrize("W,H,D,md,paths,n", SGM_CASES)
+def test_sgm_stages_bit_exact(gpu, W, H, D, md, paths, n):
+    seq = SyntheticSequence(W, H, D, min_disp=md, n_frames=4)
+    L, R = seq.batch(1, n)
+    rng = np.random.default_rng(W)
+    L[0, 5:20, 10:40] = rng.integers(0, 256, (15, 30, 3))  # some real colour
+    cfg = cb.Config(W, H, max_batch=n, num_disparities=D, min_disparity=md, paths=paths, enable_superpixels=False)
+    with cb.Context(cfg) as ctx:
+        ctx.sgm_gray_census(dev(L), dev(R))
+        ctx.sgm_aggregate(n)
+        disp = host(ctx.sgm_wta_post(n))
+        cl, cr, gl = (host(ctx.sgm_intermediate(k, n)) for k in (0, 1, 2))
+        vols = [host(ctx.sgm_intermediate(10 + p, n)) for p in range(paths)]
+        wl, wr = host(ctx.sgm_intermediate(3, n)), host(ctx.sgm_intermediate(4, n))
+        for f in range(n):
+            o_disp, inter = po.sgm_compute(L[f], R[f], D, md, paths=paths, intermediates=True)
+            assert np.array_equal(gl[f], po.gray(L[f])), "gray"
+            assert np.array_equal(cl[f], inter["census_l"]), "census left"
+            assert np.array_equal(cr[f], inter["census_r"]), "census right"
+            for p in range(paths):
+                bad = np.argwhere(vols[p][f] != inter["volumes"][p])
+                assert bad.size == 0, f"path {p} volume differs first at {bad[:3]}"
+            assert np.array_equal(wl[f], inter["left_raw"]), "WTA left"
+            assert np.array_equal(wr[f], inter["right_raw"]), "WTA right"
+            assert np.array_equal(disp[f], o_disp), "disparity"
+
+
+def test_disparity_batch_equals_single_and_is_repeatable(gpu):
+    W, H, D = 256, 64, 64
+    seq = SyntheticSequence(W, H, D, n_frames=6)
+    L, R = seq.batch(1, 5)
+    cfg = cb.Config(W, H, max_batch=5, num_disparities=D, smoothing_radius=2, smoothing_iterations=1, enable_superpixels=False)
+    with cb.Context(cfg) as ctx:
+        a = host(ctx.disparity(dev(L), dev(R)))
+        b = host(ctx.disparity(dev(L), dev(R)))
+        assert np.array_equal(a, b)
+        for f in range(5):
+            one = host(ctx.disparity(dev(L[f:f + 1]), dev(R[f:f + 1])))
+            assert np.array_equal(one[0], a[f])
+        o = po.interpolate(po.sgm_compute(L[2], R[2], D), 2, 1, 64, W)
+        assert np.array_equal(a[2], o)
+
+
+@pytest.mark.parametrize("radius,iters", [(2, 1), (3, 1), (3, 3), (4, 2)])
+@pytest.mark.parametrize("W,H", [(200, 150), (129, 65), (64, 64)])
+def test_interpolate(gpu, W, H, radius, iters):
+    rng = np.random.default_rng(radius * 10 + iters)
+    d = rng.integers(60, 900, (1, H, W)).astype(np.int16)
+    d[0][rng.random((H, W)) < 0.3] = 48
+    d[0][rng.random((H, W)) < 0.05] = -32768
+    with cb.Context(cb.Config(W, H, num_disparities=64, enable_superpixels=False)) as ctx:
+        got = host(ctx.interpolate(dev(d), radius, iters, 64, W))
+    assert np.array_equal(got[0], po.interpolate(d[0], radius, iters, 64, W))
+
+
+@pytest.mark.parametrize("W,H", [(300, 290), (128, 128), (131, 259), (50, 20)])
+def test_derivative_and_naive(gpu, W, H):
+    rng = np.random.default_rng(W + H)
+    base = (np.arange(H)[:, None] * 3 + np.arange(W)[None, :] // 7).astype(np.int16) + 64
+    d = np.stack([base + rng.integers(-3, 4, (H, W)).astype(np.int16) for _ in range(2)])
+    d[:, rng.random((H, W)) < 0.1] = -32768
+    with cb.Context(cb.Config(W, H, max_batch=2, num_disparities=64, enable_superpixels=False)) as ctx:
+        deriv, hist = ctx.derivative(dev(d))
+        nd, nh = ctx.naive_derivative(dev(d))
+        planes = ctx.classify(nd, [[1, 30, -3, 1], [2, 9, -8, 2]])
+        planes2 = ctx.classify(deriv, [[1, 30, -3, 1]])
+        for f in range(2):
+            o_d, o_h = po.derivative(d[f])
+            assert np.array_equal(host(deriv)[f], o_d)
+            assert np.array_equal(host(hist)[f], o_h)
+            o_nd, o_nh = po.naive_derivative(d[f])
+            assert np.array_equal(host(nd)[f], o_nd)
+            assert np.array_equal(host(nh)[f], o_nh)
+            pr = [1, 30, -3, 1] if f == 0 else [2, 9, -8, 2]
+            assert np.array_equal(host(planes)[f], po.classify(o_nd, *pr))
+            assert np.array_equal(host(planes2)[f], po.classify(o_d, 1, 30, -3, 1, channel_stride=2))
+
+
+@pytest.mark.parametrize("W,H,block", [(150, 140, 12), (128, 128, 16), (70, 50, 8), (333, 97, 10)])
+def test_border_map_and_block_init(gpu, W, H, block):
+    with cb.Context(cb.Config(W, H, num_disparities=64, sp_block_size=block)) as ctx:
+        n = ctx.superpixels_reset(1)
+        lab0, n0 = po.block_init(W, H, block, block)
+        assert n == n0
+        rng = np.random.default_rng(0)
+        lab = lab0.copy()
+        ys, xs = rng.integers(0, H, 400), rng.integers(0, W, 400)
+        lab[ys, xs] = rng.integers(0, n0, 400)
+        got = host(ctx.superpixels_border_map(dev(lab)))
+        assert np.array_equal(got, po.border_map(lab))
+
+
+SP_CASES = [
+    dict(W=192, H=96, block=12, its=8, kw={}),
+    dict(W=170, H=70, block=10, its=5, kw=dict(w_compact=0.03, progressive=1.0)),   # kitti-superpixels.json
+    dict(W=160, H=64, block=8, its=6, kw=dict(w_disp=0.0)),                          # disparity feature off
+]
+
+
+@pytest.mark.parametrize("case", SP_CASES, ids=lambda c: f"{c['W']}x{c['H']}b{c['block']}")
+def test_superpixel_relax_agreement(gpu, case):
+    W, H, block, its, kw = case["W"], case["H"], case["block"], case["its"], case["kw"]
+    seq = SyntheticSequence(W, H, 64, n_frames=4, tint=True)
+    cfg = cb.Config(W, H, max_batch=2, num_disparities=64, smoothing_radius=2, smoothing_iterations=1,
+                    sp_block_size=block, sp_compactness_weight=kw.get("w_compact", 0.1),
+                    sp_progressive_compactness_cost=kw.get("progressive", 0.0),
+                    sp_disparity_weight=kw.get("w_disp", 1.0))
+    with cb.Context(cfg) as ctx:
+        lab_o, nlab = po.block_init(W, H, block, block)
+        for fid in (1, 2, 3):
+            l, r, _ = seq.frame(fid)
+            disp = ctx.disparity(dev(l[None]), dev(r[None]))
+            deriv, _ = ctx.derivative(disp)
+            use_d = kw.get("w_disp", 1.0) > 0
+            got = host(ctx.superpixels_relax(dev(l[None]), deriv if use_d else None, its, slots=[1]))[0]
+            lab_o, bc, mv = po.sp_relax(lab_o, nlab, po.ycrcb(l), host(deriv)[0] if use_d else None, its, **kw)
+            agree = (got == lab_o).mean()
+            assert agree >= LABEL_AGREEMENT, (fid, agree)
+            assert mv.sum() > 0
+            # keep both chains on the oracle's state so one rounding difference cannot snowball
+            ctx.superpixels_set_labels(1, dev(lab_o))
+
+
+def test_sp_planeseg_exact(gpu):
+    W, H = 200, 120
+    rng = np.random.default_rng(4)
+    lab, n = po.block_init(W, H, 12, 12)
+    lab = np.stack([lab, np.roll(lab, 5, axis=1)])
+    deriv = rng.integers(-40, 40, (2, H, W, 2)).astype(np.int16)
+    deriv[rng.random((2, H, W)) < 0.2] = -32768
+    with cb.Context(cb.Config(W, H, max_batch=2, num_disparities=64)) as ctx:
+        unsm, planes = ctx.sp_planeseg(dev(deriv), dev(lab), [[1, 30, -3, 1], [0, 5, -20, 0]])
+        for f, pr in enumerate([[1, 30, -3, 1], [0, 5, -20, 0]]):
+            ou, op = po.sp_planeseg(deriv[f], lab[f], n, *pr)
+            assert np.array_equal(host(unsm)[f], ou) and np.array_equal(host(planes)[f], op)
+    # the reference refuses more than 5461 superpixels (sp_planeseg.cu:327-331)
+    with cb.Context(cb.Config(640, 480, num_disparities=64, sp_block_size=6)) as ctx:
+        with pytest.raises(cb.CartB200Error) as e:
+            ctx.sp_planeseg(dev(np.zeros((1, 480, 640, 2), np.int16)), dev(np.zeros((1, 480, 640), np.uint16)), [[0, 0, 0, 0]])
+        assert e.value.code == cb.E_UNSUPPORTED
+
+
+def _frames(W, H, D, n, tint=False):
+    seq = SyntheticSequence(W, H, D, n_frames=n, tint=tint)
+    return seq, [seq.frame(i + 1)[:2] for i in range(n)]
+
+
+@pytest.mark.parametrize("provider", ["static", "histogram_peak"])
+def test_sequence_naive_pipeline(gpu, provider):
+    W, H, D, n = 192, 96, 64, 23
+    seq, frames = _frames(W, H, D, n)
+    cfgd = dict(D=D, radius=2, iters=1)
+    ref = rp.naive_sequence(frames, cfgd, provider=provider, update=5, reset=2)
+    L = np.stack([f[0] for f in frames])
+    R = np.stack([f[1] for f in frames])
+    cfg = cb.Config(W, H, max_batch=4, num_disparities=D, smoothing_radius=2, smoothing_iterations=1, enable_superpixels=False)
+    opts = cb.SequenceOptions(pipeline=0, provider=0 if provider == "static" else 1, update_interval=5, reset_interval=2)
+    with cb.Context(cfg) as ctx:
+        planes, disp = ctx.run_sequence_host(opts, L, R, want_disparity=True)
+        pd = host(ctx.run_sequence_device(opts, dev(L), dev(R)))
+    for i in range(n):
+        assert np.array_equal(disp[i], ref[i]["disparity"]), i
+        assert np.array_equal(planes[i], ref[i]["planes"]), (i, ref[i]["params"])
+    assert np.array_equal(pd, planes)
+    if provider == "histogram_peak":
+        assert any(r["params"][2:] != [0, 0, 0, 0] for r in ref), "peak provider never fired on the test data"
+
+
+@pytest.mark.parametrize("provider", ["static", "histogram_peak"])
+def test_sequence_superpixel_pipeline(gpu, provider):
+    # reset every 8 frames so that 21 frames span chunks [1..7], [8..15], [16..21]; 2 slots force two groups
+    W, H, D, n = 160, 64, 64, 21
+    seq, frames = _frames(W, H, D, n, tint=True)
+    cfgd = dict(D=D, radius=2, iters=1)
+    ref = rp.sp_sequence(frames, cfgd, provider=provider, update=5, reset=2, initial=6, steady=3, sp_reset=8, block=8)
+    L = np.stack([f[0] for f in frames])
+    R = np.stack([f[1] for f in frames])
+    cfg = cb.Config(W, H, max_batch=2, num_disparities=D, smoothing_radius=2, smoothing_iterations=1, sp_block_size=8)
+    opts = cb.SequenceOptions(pipeline=1, provider=0 if provider == "static" else 1, update_interval=5, reset_interval=2,
+                              sp_initial_iterations=6, sp_iterations=3, sp_reset_iterations=8)
+    with cb.Context(cfg) as ctx:
+        planes, disp = ctx.run_sequence_host(opts, L, R, want_disparity=True)
+        pd = host(ctx.run_sequence_device(opts, dev(L), dev(R)))
+    agree = []
+    for i in range(n):
+        assert np.array_equal(disp[i], ref[i]["disparity"]), i
+        agree.append((planes[i] == ref[i]["planes"]).mean())
+    # plane labels inherit the superpixel tolerance (majority vote over near-identical superpixels)
+    assert min(agree) >= 0.995 and np.mean(agree) >= LABEL_AGREEMENT, agree
+    assert np.array_equal(pd, planes)
+
+
+def test_full_size_kitti_properties(gpu):
+    """BASELINE.json full size (1242x375, D=128): size-independent properties instead of the slow oracle."""
+    W, H, D = 1242, 375, 128
+    seq = SyntheticSequence(W, H, D, n_frames=4)
+    L, R = seq.batch(1, 3)
+    gts = [seq.frame(i)[2] for i in (1, 2, 3)]
+    cfg = cb.Config(W, H, max_batch=3, num_disparities=D, smoothing_radius=2, smoothing_iterations=1)
+    with cb.Context(cfg) as ctx:
+        n = ctx.sgm_gray_census(dev(L), dev(R))
+        ctx.sgm_aggregate(n)
+        disp = ctx.sgm_wta_post(n)
+        vols = [ctx.sgm_intermediate(10 + p, n) for p in range(4)]
+        cl = host(ctx.sgm_intermediate(0, n))
+        # path volumes: L >= C on the first pixel of every path means equality; bounded by 31 + P2
+        for v in vols:
+            assert int(v.max()) <= 31 + 120
+        # L->R path at x = 0 and T->B path at y = 0 equal the raw matching cost there: census border is 0
+        assert int(vols[2][:, 0].max()) == 0 and int(vols[3][:, H - 1].max()) == 0
+        # left/right symmetric checksum: sum over d of the horizontal volumes is direction independent at row ends
+        d = host(disp)
+        for f in range(3):
+            valid = d[f] != 48
+            valid &= d[f] != -32768
+            err = np.abs(d[f].astype(np.float32) / 16 - gts[f])
+            assert valid.mean() > 0.6 and (err[valid] <= 1).mean() > 0.9, (f, valid.mean(), (err[valid] <= 1).mean())
+        deriv, hist = ctx.derivative(disp)
+        hv = host(hist)
+        dv = host(deriv)
+        for f in range(3):
+            for ch in range(2):
+                ok = (dv[f, :, :, ch] != -32768) & (dv[f, :, :, ch] >= -128) & (dv[f, :, :, ch] <= 127)
+                assert hv[f, :, ch].sum() == ok.sum()            # histogram mass = in-range valid pixels
+                assert np.array_equal(np.bincount(dv[f, :, :, ch][ok].astype(np.int64) + 128, minlength=256), hv[f, :, ch])
+        # one frame end-to-end against the oracle at full size (a few seconds of CPU)
+        o = po.interpolate(po.sgm_compute(L[1], R[1], D), 2, 1, 64, W)
+        assert np.array_equal(d[1], o)
+        labels = ctx.superpixels_relax(dev(L[:1]), deriv[:1], 8)
+        lab0, nlab = po.block_init(W, H, 12, 12)
+        o_lab, _, _ = po.sp_relax(lab0, nlab, po.ycrcb(L[0]), dv[0], 8)
+        assert (host(labels)[0] == o_lab).mean() >= LABEL_AGREEMENT

@@ -199,8 +199,11 @@ def test_histogram_peak_update_product_matches_oracle():
         assert (uo, po_) == (up, pp), (t, po_, pp)
         hits += uo
     assert hits > 50
-    # a flat histogram has a single peak -> early return, parameters untouched
-    assert cb.histogram_peak_update(np.full(256, 7), [0, 0, 9, 9, 9, 9]) == (False, [0, 0, 9, 9, 9, 9])
+    # a flat histogram (all ties): the early returns fire, the ranges stay untouched, and the product
+    # resolves the std::sort ties exactly like the oracle does
+    flat = cb.histogram_peak_update(np.full(256, 7), [0, 0, 9, 9, 9, 9])
+    assert flat == po.histogram_peak_update(np.full(256, 7), [0, 0, 9, 9, 9, 9])
+    assert flat[0] is False and flat[1][2:] == [9, 9, 9, 9]
 
 
 def test_find_peaks_toy():
