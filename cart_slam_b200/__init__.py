@@ -38,7 +38,7 @@ class CartB200Error(RuntimeError):
 
 class _CConfig(C.Structure):
     _fields_ = [
-        ("width", C.c_int), ("height", C.c_int), ("max_batch", C.c_int),
+        ("width", C.c_int), ("height", C.c_int), ("max_batch", C.c_int), ("enable_sgm", C.c_int),
         ("min_disparity", C.c_int), ("num_disparities", C.c_int), ("p1", C.c_int), ("p2", C.c_int),
         ("uniqueness_ratio", C.c_int), ("paths", C.c_int), ("smoothing_radius", C.c_int),
         ("smoothing_iterations", C.c_int), ("enable_superpixels", C.c_int), ("sp_block_size", C.c_int),
@@ -126,6 +126,7 @@ class Config:
     width: int
     height: int
     max_batch: int = 1
+    enable_sgm: bool = True
     min_disparity: int = 4
     num_disparities: int = 256
     p1: int = 10

@@ -62,6 +62,14 @@ int ensureCap(cartb200_ctx* c, T** p, size_t* cap, size_t bytes) {
 int* slotIota(cartb200_ctx* c) { return reinterpret_cast<int*>(c->paramsDev + 4 * (size_t)c->B); }
 int* slotScratch(cartb200_ctx* c) { return slotIota(c) + c->B; }
 
+int checkSgm(cartb200_ctx* c) {
+    if (!c->volumes) {
+        c->err = "context created with enable_sgm = 0";
+        return CARTB200_E_ARG;
+    }
+    return CARTB200_OK;
+}
+
 int checkBatch(cartb200_ctx* c, int n) {
     if (!c) return CARTB200_E_ARG;
     if (n < 1 || n > c->B) {
@@ -82,6 +90,7 @@ void cartb200_default_config(cartb200_config* cfg, int width, int height) {
     cfg->width = width;
     cfg->height = height;
     cfg->max_batch = 1;
+    cfg->enable_sgm = 1;
     cfg->min_disparity = 4;       // cartconfig.cpp:147
     cfg->num_disparities = 256;   // cartconfig.cpp:148
     cfg->p1 = 10;                 // cv::cuda::createStereoSGM defaults
@@ -159,13 +168,15 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
     c->dispPitch = alignUp(W * 2, 128);
     c->volFrameStride = H * W * (size_t)c->D;
     c->volPathStride = c->volFrameStride * B;
-    if ((rc = devAlloc(c, &c->grayL, B * H * c->grayPitch))) return fail(rc);
-    if ((rc = devAlloc(c, &c->censusL, B * H * c->censusPitch))) return fail(rc);
-    if ((rc = devAlloc(c, &c->censusR, B * H * c->censusPitch))) return fail(rc);
-    if ((rc = devAlloc(c, &c->volumes, c->volPathStride * c->P))) return fail(rc);
-    if ((rc = devAlloc(c, &c->wtaL, B * H * c->dispPitch))) return fail(rc);
-    if ((rc = devAlloc(c, &c->wtaR, B * H * c->dispPitch))) return fail(rc);
-    if ((rc = devAlloc(c, &c->medL, B * H * c->dispPitch))) return fail(rc);
+    if (cfg->enable_sgm) {
+        if ((rc = devAlloc(c, &c->grayL, B * H * c->grayPitch))) return fail(rc);
+        if ((rc = devAlloc(c, &c->censusL, B * H * c->censusPitch))) return fail(rc);
+        if ((rc = devAlloc(c, &c->censusR, B * H * c->censusPitch))) return fail(rc);
+        if ((rc = devAlloc(c, &c->volumes, c->volPathStride * c->P))) return fail(rc);
+        if ((rc = devAlloc(c, &c->wtaL, B * H * c->dispPitch))) return fail(rc);
+        if ((rc = devAlloc(c, &c->wtaR, B * H * c->dispPitch))) return fail(rc);
+    }
+    if ((rc = devAlloc(c, &c->medL, B * H * c->dispPitch))) return fail(rc);  // also the interpolation staging image
     // paramsDev [B][4] + slot iota [B] + slot scratch [B]
     if ((rc = devAlloc(c, &c->paramsDev, (4 * B + 2 * B) * sizeof(int32_t)))) return fail(rc);
     {
@@ -255,6 +266,7 @@ int cartb200_sgm_gray_census(cartb200_ctx* c, int n, const uint8_t* l, const uin
                              void* stream) {
     int rc = checkBatch(c, n);
     if (rc) return rc;
+    if ((rc = checkSgm(c))) return rc;
     if (!l || !r || pitch < (size_t)c->W * 3) {
         c->err = "gray_census: bad image arguments";
         return CARTB200_E_ARG;
@@ -266,6 +278,7 @@ int cartb200_sgm_gray_census(cartb200_ctx* c, int n, const uint8_t* l, const uin
 int cartb200_sgm_aggregate(cartb200_ctx* c, int n, void* stream) {
     int rc = checkBatch(c, n);
     if (rc) return rc;
+    if ((rc = checkSgm(c))) return rc;
     return launch_aggregate(c, n, (cudaStream_t)stream);
 }
 
@@ -284,6 +297,7 @@ int cartb200_interpolate(cartb200_ctx* c, int n, int16_t* d, size_t pitch, size_
 int cartb200_sgm_wta_post(cartb200_ctx* c, int n, int16_t* d, size_t pitch, size_t fstride, void* stream) {
     int rc = checkBatch(c, n);
     if (rc) return rc;
+    if ((rc = checkSgm(c))) return rc;
     if (!d || pitch < (size_t)c->W * 2) {
         c->err = "wta_post: bad image arguments";
         return CARTB200_E_ARG;

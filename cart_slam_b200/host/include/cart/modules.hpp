@@ -1,0 +1,168 @@
+// The hot-path modules of CART-SLAM, same names / constructor parameters / data keys as the reference,
+// each one a thin host shell around the cartb200 C ABI (include/cartb200.h):
+//   ImageDisparityModule                          /root/reference/include/modules/disparity.hpp:24-44
+//   ImageDisparityDerivativeModule                /root/reference/include/modules/disparity.hpp:70-79
+//   SuperPixelModule                              /root/reference/include/modules/superpixels.hpp:15-41
+//   PlaneParameters / providers                   /root/reference/include/modules/planeseg.hpp:25-113
+//   DisparityPlaneSegmentationModule              /root/reference/include/modules/planeseg.hpp:115-162
+//   SuperPixelDisparityPlaneSegmentationModule    /root/reference/include/modules/planeseg.hpp:164-186
+// Temporal smoothing (optical flow) is outside the hot-path scope: requesting it throws.
+#pragma once
+#include <cmath>
+
+#include "cart/core.hpp"
+
+struct cartb200_ctx;
+
+#define CARTSLAM_KEY_DISPARITY "disparity"
+#define CARTSLAM_KEY_DISPARITY_DERIVATIVE "disparity_derivative"
+#define CARTSLAM_KEY_DISPARITY_DERIVATIVE_HISTOGRAM "disparity_derivative_histogram"
+#define CARTSLAM_KEY_SUPERPIXELS "superpixels"
+#define CARTSLAM_KEY_SUPERPIXELS_MAX_LABEL "superpixels_max_label"
+#define CARTSLAM_KEY_PLANES "planes"
+#define CARTSLAM_KEY_PLANES_UNSMOOTHED "planes_unsmoothed"
+#define CARTSLAM_KEY_PLANE_PARAMETERS "plane_parameters"
+#define CARTSLAM_KEY_DISPARITY_DERIVATIVE_HIST "disp_derivative_histogram"
+#define CARTSLAM_DISPARITY_INVALID (-32768)
+#define CARTSLAM_PLANE_COUNT 3
+#define CARTSLAM_PLANE_TEMPORAL_DISTANCE_DEFAULT 3
+
+namespace cart {
+
+typedef int16_t disparity_t;
+typedef int16_t derivative_t;
+namespace contour {
+typedef uint16_t label_t;
+}
+
+// RAII handle on a cartb200 context; throws std::runtime_error with cartb200_last_error on failure.
+class Kernels {
+   public:
+    Kernels(Size size, bool sgm, bool superpixels, int minDisparity = 4, int numDisparities = 256, int smoothingRadius = -1,
+            int smoothingIterations = 5, int spBlockSize = 12, double direct = 0.5, double diagonal = 0.5 / std::sqrt(2.0),
+            double wCompact = 0.1, double progressive = 0.0, double wImage = 1.5, double wDisparity = 1.0);
+    ~Kernels();
+    Kernels(const Kernels&) = delete;
+    cartb200_ctx* get() const { return ctx; }
+    void check(int rc, const char* what) const;
+    std::mutex mutex;  // a context is not thread-safe; modules serialise their frames on it
+
+   private:
+    cartb200_ctx* ctx = nullptr;
+};
+
+class ImageDisparityModule : public SyncWrapperSystemModule {
+   public:
+    ImageDisparityModule(const Size imageRes, int minDisparity = 4, int numDisparities = 256, int blockSize = 3,
+                         int smoothingRadius = -1, int smoothingIterations = 5);
+    system_data_t runInternal(System& system, SystemRunData& data) override;
+
+   private:
+    std::unique_ptr<Kernels> kernels;
+};
+
+class ImageDisparityDerivativeModule : public SyncWrapperSystemModule {
+   public:
+    ImageDisparityDerivativeModule();
+    system_data_t runInternal(System& system, SystemRunData& data) override;
+
+   private:
+    std::unique_ptr<Kernels> kernels;  // created lazily: the image size is only known from the data
+};
+
+class SuperPixelModule : public SyncWrapperSystemModule {
+   public:
+    SuperPixelModule(const Size imageRes, const unsigned int initialIterations = 18, const unsigned int iterations = 6,
+                     const unsigned int blockSize = 12, const unsigned int resetIterations = 64,
+                     const double directCliqueCost = 0.5, const double diagonalCliqueCost = 0.5 / std::sqrt(2.0),
+                     const double compactnessWeight = 0.05, const double progressiveCompactnessCost = 0.0,
+                     const double imageWeight = 1.0, const double disparityWeight = 1.25);
+    system_data_t runInternal(System& system, SystemRunData& data) override;
+
+   private:
+    std::unique_ptr<Kernels> kernels;
+    const unsigned int initialIterations, iterations, resetIterations, blockSize;
+    const bool requiresDisparityDerivative;
+    contour::label_t maxLabelId = 0;
+};
+
+struct PlaneParameters {
+    PlaneParameters(int horizontalCenter, int verticalCenter, std::pair<int, int> horizontalRange, std::pair<int, int> verticalRange)
+        : horizontalRange(horizontalRange), verticalRange(verticalRange), horizontalCenter(horizontalCenter), verticalCenter(verticalCenter) {}
+    const std::pair<int, int> horizontalRange, verticalRange;
+    const int horizontalCenter, verticalCenter;
+};
+
+enum Plane { HORIZONTAL = 0, VERTICAL = 1, UNKNOWN = 2 };
+
+class PlaneParameterProvider {
+   public:
+    virtual ~PlaneParameterProvider() = default;
+    PlaneParameters getPlaneParameters() const { return PlaneParameters(horizontalCenter, verticalCenter, horizontalRange, verticalRange); }
+    // histogram: 256 bins (bin = derivative + 128)
+    virtual void updatePlaneParameters(System& system, SystemRunData& data, const std::vector<int32_t>& histogram) = 0;
+
+   protected:
+    PlaneParameterProvider(int horizontalCenter = 0, int verticalCenter = 0, std::pair<int, int> horizontalRange = {0, 0},
+                           std::pair<int, int> verticalRange = {0, 0})
+        : horizontalRange(horizontalRange), verticalRange(verticalRange), horizontalCenter(horizontalCenter), verticalCenter(verticalCenter) {}
+    std::pair<int, int> horizontalRange, verticalRange;
+    int horizontalCenter, verticalCenter;
+};
+
+class HistogramPeakPlaneParameterProvider : public PlaneParameterProvider {
+   public:
+    void updatePlaneParameters(System& system, SystemRunData& data, const std::vector<int32_t>& histogram) override;
+};
+
+class StaticPlaneParameterProvider : public PlaneParameterProvider {
+   public:
+    StaticPlaneParameterProvider(int horizontalCenter, int verticalCenter, std::pair<int, int> horizontalRange, std::pair<int, int> verticalRange)
+        : PlaneParameterProvider(horizontalCenter, verticalCenter, horizontalRange, verticalRange) {}
+    void updatePlaneParameters(System&, SystemRunData&, const std::vector<int32_t>&) override {}
+};
+
+class DisparityPlaneSegmentationModule : public SyncWrapperSystemModule {
+   public:
+    DisparityPlaneSegmentationModule(std::shared_ptr<PlaneParameterProvider> planeParameterProvider, const int updateInterval = 30,
+                                     const int resetInterval = 10, const bool useTemporalSmoothing = false,
+                                     const unsigned int temporalSmoothingDistance = CARTSLAM_PLANE_TEMPORAL_DISTANCE_DEFAULT);
+    system_data_t runInternal(System& system, SystemRunData& data) override;
+
+   private:
+    void updatePlaneParameters(System& system, SystemRunData& data);
+    const int updateInterval, resetInterval;
+    std::shared_ptr<PlaneParameterProvider> planeParameterProvider;
+    std::unique_ptr<Kernels> kernels;
+    std::mutex derivativeHistogramMutex;
+    std::vector<int64_t> derivativeHistogram;  // running total (the reference keeps it on the GPU)
+};
+
+class SuperPixelDisparityPlaneSegmentationModule : public SyncWrapperSystemModule {
+   public:
+    SuperPixelDisparityPlaneSegmentationModule(std::shared_ptr<PlaneParameterProvider> planeParameterProvider,
+                                               const int updateInterval = 30, const int resetInterval = 10,
+                                               const bool useTemporalSmoothing = false,
+                                               const unsigned int temporalSmoothingDistance = CARTSLAM_PLANE_TEMPORAL_DISTANCE_DEFAULT);
+    system_data_t runInternal(System& system, SystemRunData& data) override;
+
+   private:
+    void updatePlaneParameters(System& system, SystemRunData& data);
+    const int updateInterval, resetInterval;
+    std::shared_ptr<PlaneParameterProvider> planeParameterProvider;
+    std::unique_ptr<Kernels> kernels;
+    std::mutex derivativeHistogramMutex;
+    bool histogramCreated = false;
+    std::vector<int64_t> derivativeHistogram;
+};
+
+// ---- configuration (same JSON keys and defaults as /root/reference/src/cartconfig.cpp:56-228) --------
+namespace config {
+// Module types outside the hot-path scope (visualisation, optflow, depth, features, planefit, ...) are
+// rejected with std::runtime_error unless skipOutOfScope is set, in which case they are skipped with a warning
+// and `use_temporal_smoothing` is forced off.
+void applyModuleConfigText(const std::string& jsonText, std::shared_ptr<System> system, bool skipOutOfScope = false);
+void readModuleConfig(const std::string& path, std::shared_ptr<System> system, bool skipOutOfScope = false);
+}  // namespace config
+
+}  // namespace cart

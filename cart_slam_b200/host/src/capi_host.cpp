@@ -1,0 +1,69 @@
+// C entry point of the module layer, used by the tests (ctypes) and by integrators who want the whole
+// reference-shaped pipeline behind one call: builds a System from a JSON module list (the reference's
+// config/modules/*.json schema), feeds it `n` frames from host memory in id order, returns the planes.
+#include <cstring>
+#include <deque>
+#include <exception>
+#include <string>
+
+#include "cart/modules.hpp"
+
+namespace {
+std::string g_error;
+void describe(const std::exception& e, std::string& out, int depth = 0) {
+    out += std::string(depth ? " <- " : "") + e.what();
+    try {
+        std::rethrow_if_nested(e);
+    } catch (const std::exception& n) {
+        describe(n, out, depth + 1);
+    } catch (...) {
+    }
+}
+}  // namespace
+
+extern "C" {
+
+const char* cartb200_host_last_error() { return g_error.c_str(); }
+
+// sequential != 0: wait for each frame before starting the next (the canonical in-order schedule);
+// 0: up to CARTSLAM_CONCURRENT_RUN_LIMIT frames in flight like the reference's main loop.
+// planes_out: n x H x W u8 (key "planes"); labels_out (nullable): n x H x W u16 (key "superpixels");
+// disparity_out (nullable): n x H x W s16.
+int cartb200_host_run_config(const char* modules_json, int skip_out_of_scope, int width, int height, int n,
+                             const uint8_t* left_bgr, const uint8_t* right_bgr, int sequential, uint8_t* planes_out,
+                             uint16_t* labels_out, int16_t* disparity_out) {
+    using namespace cart;
+    try {
+        auto source = std::make_shared<MemoryDataSource>(Size(width, height), n, left_bgr, right_bgr);
+        auto system = std::make_shared<System>(source);
+        config::applyModuleConfigText(modules_json, system, skip_out_of_scope != 0);
+        const size_t px = (size_t)width * height;
+        std::deque<std::pair<uint32_t, std::future<void>>> inflight;
+        auto collect = [&]() {
+            const uint32_t fid = inflight.front().first;
+            inflight.front().second.get();
+            inflight.pop_front();
+            auto run = system->getRunById(fid);  // still retained: we lag by < CARTSLAM_RUN_RETENTION frames
+            if (planes_out && run->hasData(CARTSLAM_KEY_PLANES))
+                run->getData<image_t>(CARTSLAM_KEY_PLANES)->download(planes_out + px * (fid - 1), (size_t)width);
+            if (labels_out && run->hasData(CARTSLAM_KEY_SUPERPIXELS))
+                run->getData<image_t>(CARTSLAM_KEY_SUPERPIXELS)->download(labels_out + px * (fid - 1), (size_t)width * 2);
+            if (disparity_out && run->hasData(CARTSLAM_KEY_DISPARITY))
+                run->getData<image_t>(CARTSLAM_KEY_DISPARITY)->download(disparity_out + px * (fid - 1), (size_t)width * 2);
+        };
+        uint32_t id = 0;
+        while (!source->isFinished()) {
+            auto f = system->run();
+            inflight.emplace_back(++id, std::move(f));
+            if (sequential || inflight.size() >= CARTSLAM_CONCURRENT_RUN_LIMIT) collect();
+        }
+        while (!inflight.empty()) collect();
+        return 0;
+    } catch (const std::exception& e) {
+        g_error.clear();
+        describe(e, g_error);
+        return -1;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+// Host runtime of the module layer: device images, data containers, thread pool, data sources and the
+// System scheduler (dependency wait -> module run -> insert results), restating
+// /root/reference/src/cartslam.cpp:65-333, /root/reference/src/utils/data.cpp:7-56,
+// /root/reference/src/modules/module.cpp:7-27 and /root/reference/src/datasource.cpp:19-56 on std:: primitives.
+#include "cart/core.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+
+namespace cart {
+
+void logMessage(const char* level, const std::string& who, const std::string& what) {
+    static std::mutex m;
+    static const bool quiet = std::getenv("CARTB200_QUIET") != nullptr;
+    if (quiet && level[0] == 'I') return;
+    std::lock_guard<std::mutex> lock(m);
+    std::fprintf(stderr, "[%s] %s: %s\n", level, who.c_str(), what.c_str());
+}
+
+static void cudaCheck(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+size_t imageElemBytes(ImageType t) {
+    switch (t) {
+        case IMG_8UC1: return 1;
+        case IMG_8UC3: return 3;
+        case IMG_16SC1: return 2;
+        case IMG_16SC2: return 4;
+        case IMG_16UC1: return 2;
+        case IMG_32SC1: return 4;
+        case IMG_32SC2: return 8;
+    }
+    return 1;
+}
+
+DeviceImage::Buf::~Buf() {
+    if (p) cudaFree(p);
+}
+
+DeviceImage::DeviceImage(int rows_, int cols_, ImageType type_) : rows(rows_), cols(cols_), type(type_) {
+    buf = std::make_shared<Buf>();
+    cudaCheck(cudaMallocPitch(&buf->p, &pitch, (size_t)cols * imageElemBytes(type), rows), "cudaMallocPitch");
+}
+
+void DeviceImage::upload(const void* host, size_t hostPitch, void* stream) {
+    cudaCheck(cudaMemcpy2DAsync(ptr(), pitch, host, hostPitch, (size_t)cols * imageElemBytes(type), rows,
+                                cudaMemcpyHostToDevice, (cudaStream_t)stream),
+              "upload");
+}
+
+void DeviceImage::download(void* host, size_t hostPitch, void* stream) const {
+    cudaCheck(cudaMemcpy2DAsync(host, hostPitch, ptr(), pitch, (size_t)cols * imageElemBytes(type), rows,
+                                cudaMemcpyDeviceToHost, (cudaStream_t)stream),
+              "download");
+    cudaCheck(cudaStreamSynchronize((cudaStream_t)stream), "download sync");
+}
+
+// ---- thread pool -----------------------------------------------------------------------------------
+ThreadPool::ThreadPool(size_t n) {
+    for (size_t i = 0; i < std::max<size_t>(1, n); ++i) workers.emplace_back([this] { work(); });
+}
+
+ThreadPool::~ThreadPool() {
+    {
+        std::lock_guard<std::mutex> lock(m);
+        stop = true;
+    }
+    cv.notify_all();
+    for (auto& w : workers) w.join();
+}
+
+void ThreadPool::post(std::function<void()> fn) {
+    {
+        std::lock_guard<std::mutex> lock(m);
+        queue.push_back(std::move(fn));
+    }
+    cv.notify_one();
+}
+
+void ThreadPool::work() {
+    for (;;) {
+        std::function<void()> fn;
+        {
+            std::unique_lock<std::mutex> lock(m);
+            cv.wait(lock, [this] { return stop || !queue.empty(); });
+            if (stop && queue.empty()) return;
+            fn = std::move(queue.front());
+            queue.pop_front();
+            ++busy;
+        }
+        fn();
+        {
+            std::lock_guard<std::mutex> lock(m);
+            --busy;
+        }
+        idleCv.notify_all();
+    }
+}
+
+void ThreadPool::join() {
+    std::unique_lock<std::mutex> lock(m);
+    idleCv.wait(lock, [this] { return queue.empty() && busy == 0; });
+}
+
+// ---- data container --------------------------------------------------------------------------------
+bool DataContainer::hasData(const std::string& key) {
+    std::lock_guard<std::mutex> lock(dataMutex);
+    return data.count(key) != 0;
+}
+
+std::vector<std::string> DataContainer::getDataKeys() {
+    std::lock_guard<std::mutex> lock(dataMutex);
+    std::vector<std::string> keys;
+    for (const auto& p : data) keys.push_back(p.first);
+    return keys;
+}
+
+void DataContainer::insertData(system_data_pair_t entry) {
+    {
+        std::lock_guard<std::mutex> lock(dataMutex);
+        data[entry.first] = entry.second;
+    }
+    dataCondition.notify_all();
+}
+
+void DataContainer::waitForData(const std::vector<std::string>& keys) {
+    if (keys.empty()) throw std::invalid_argument("No keys provided to wait for");
+    for (const auto& key : keys) {
+        std::unique_lock<std::mutex> lock(dataMutex);
+        // a wait of more than a few seconds means the producing run has failed (data.cpp:41-49)
+        if (!dataCondition.wait_for(lock, std::chrono::seconds(CARTSLAM_WAIT_FOR_DATA_TIMEOUT),
+                                    [this, &key] { return data.count(key) != 0; }))
+            throw DataNotAvailableException(key);
+    }
+}
+
+// ---- data sources ----------------------------------------------------------------------------------
+image_t getReferenceImage(std::shared_ptr<DataElement> element) {
+    switch (element->type) {
+        case STEREO: return std::static_pointer_cast<StereoDataElement>(element)->left;
+        default: throw std::runtime_error("Unknown data element type");
+    }
+}
+
+std::shared_ptr<DataElement> DataSource::getNext(void* stream) {
+    if (!isNextReady()) throw std::runtime_error("Next element is not ready!");
+    auto element = getNextInternal(stream);
+    if (element->type == STEREO) {
+        auto st = std::static_pointer_cast<StereoDataElement>(element);
+        if (st->left.type != IMG_8UC3 || st->right.type != IMG_8UC3)  // datasource.cpp:6-16 forces CV_8UC3
+            throw std::runtime_error("stereo images must be CV_8UC3 BGR");
+    }
+    return element;
+}
+
+std::shared_ptr<DataElement> MemoryDataSource::getNextInternal(void* stream) {
+    const size_t frame = (size_t)imageSize.width * imageSize.height * 3;
+    image_t l(imageSize.height, imageSize.width, IMG_8UC3), r(imageSize.height, imageSize.width, IMG_8UC3);
+    l.upload(left + frame * next, (size_t)imageSize.width * 3, stream);
+    r.upload(right + frame * next, (size_t)imageSize.width * 3, stream);
+    cudaCheck(cudaStreamSynchronize((cudaStream_t)stream), "frame upload");
+    ++next;
+    return std::make_shared<StereoDataElement>(l, r);
+}
+
+// ---- modules ---------------------------------------------------------------------------------------
+std::future<system_data_t> SyncWrapperSystemModule::run(System& system, SystemRunData& data) {
+    auto task = std::make_shared<std::packaged_task<system_data_t()>>([this, &system, &data] { return runInternal(system, data); });
+    auto future = task->get_future();
+    system.getThreadPool().post([task] { (*task)(); });
+    return future;
+}
+
+// ---- system ----------------------------------------------------------------------------------------
+std::shared_ptr<SystemRunData> SystemRunData::getRelativeRun(int8_t offset) {
+    if ((int)id + offset <= 0) throw std::invalid_argument("Offset " + std::to_string(offset) + " out of range");
+    return system->getRunById(id + offset);
+}
+
+System::System(std::shared_ptr<DataSource> source, size_t workerThreads, size_t runRetention_, size_t concurrentRunLimit_)
+    : runRetention(runRetention_), concurrentRunLimit(concurrentRunLimit_), threadPool(workerThreads), dataSource(source) {}
+
+System::~System() { threadPool.join(); }
+
+void System::addModule(std::shared_ptr<SystemModule> module) {
+    modules.push_back(module);
+    CART_LOG_INFO("System", "Added module " + module->name);
+    for (const auto& provides : module->getProvidedData()) dataProvidedBy[provides] = module;
+}
+
+void System::verifyDependencies() {
+    if (verifiedDependencies) return;
+    for (const auto& module : modules)
+        for (const auto& dep : module->getRequiredData())
+            if (dataProvidedBy.find(dep.name) == dataProvidedBy.end())
+                throw std::invalid_argument("Module " + module->name + " requires data " + dep.name +
+                                            " which is not provided by any module");
+    verifiedDependencies = true;
+}
+
+// Groups the keys by run offset and waits for each group on the run that owns it (cartslam.cpp:96-167).
+void System::waitForDependencies(const std::vector<module_dependency_t>& deps, std::shared_ptr<SystemRunData> data) {
+    std::map<int, std::vector<std::string>, std::greater<int>> byOffset;
+    for (const auto& d : deps) {
+        if ((int)data->id + d.runOffset <= 0) continue;  // the run does not exist (first frames)
+        byOffset[d.runOffset].push_back(d.name);
+    }
+    for (auto& group : byOffset) {
+        std::shared_ptr<SystemRunData> run = group.first < 0 ? data->getRelativeRun((int8_t)group.first) : data;
+        try {
+            run->waitForData(group.second);
+        } catch (const std::exception&) {
+            std::throw_with_nested(std::runtime_error("Error waiting for dependencies for run ID " + std::to_string(data->id) +
+                                                      " from run ID " + std::to_string(run->id)));
+        }
+    }
+}
+
+uint8_t System::getActiveRunCount() {
+    for (size_t i = 0; i < runs.size(); ++i)
+        if (!runs[i]->isComplete()) return (uint8_t)(runs.size() - i);
+    return 0;
+}
+
+std::shared_ptr<SystemRunData> System::startNewRun(void* stream) {
+    verifyDependencies();
+    std::unique_lock<std::mutex> lock(runMutex);
+    auto element = dataSource->getNext(stream);
+    auto data = std::make_shared<SystemRunData>(++runId, this, element);
+    runCondition.wait(lock, [this] { return getActiveRunCount() < concurrentRunLimit; });
+    runs.push_back(data);
+    if (runs.size() > runRetention) runs.erase(runs.begin());
+    return data;
+}
+
+std::shared_ptr<SystemRunData> System::getRunById(uint32_t id) {
+    std::lock_guard<std::mutex> lock(runMutex);
+    if (id > runId) throw std::invalid_argument("Index " + std::to_string(id) + " out of range (too new)");
+    if (runs.empty() || id < runs[0]->id) throw std::invalid_argument("Index " + std::to_string(id) + " out of range (too old)");
+    return runs[id - runs[0]->id];
+}
+
+std::future<void> System::run() {
+    if (modules.empty()) throw std::invalid_argument("No modules have been added to the system");
+    std::shared_ptr<SystemRunData> runData = startNewRun(nullptr);
+    struct Pending {
+        std::promise<void> done;
+        std::atomic<size_t> left;
+        std::mutex m;
+        std::exception_ptr error;
+    };
+    auto pending = std::make_shared<Pending>();
+    pending->left = modules.size();
+    auto future = pending->done.get_future();
+    for (auto module : modules) {
+        // one task per module and frame: wait for its inputs, run it, publish its outputs (cartslam.cpp:255-302)
+        threadPool.post([this, module, runData, pending] {
+            try {
+                waitForDependencies(module->getRequiredData(), runData);
+                system_data_t out = module->run(*this, *runData).get();
+                for (auto& entry : out) runData->insertData(entry);
+            } catch (...) {
+                try {
+                    std::throw_with_nested(std::runtime_error("Error running module \"" + module->name + "\" for run ID " +
+                                                              std::to_string(runData->id)));
+                } catch (...) {
+                    std::lock_guard<std::mutex> lock(pending->m);
+                    if (!pending->error) pending->error = std::current_exception();
+                }
+            }
+            if (--pending->left == 0) {
+                runData->markAsComplete();
+                {
+                    std::lock_guard<std::mutex> lock(runMutex);
+                }
+                runCondition.notify_all();
+                if (pending->error)
+                    pending->done.set_exception(pending->error);
+                else
+                    pending->done.set_value();
+            }
+        });
+    }
+    return future;
+}
+
+}  // namespace cart

@@ -47,7 +47,8 @@ typedef struct cartb200_ctx cartb200_ctx;
 typedef struct cartb200_config {
     int width, height;
     int max_batch; /* frames per batched call (scratch is sized for this) */
-    /* disparity */
+    /* disparity (enable_sgm = 0 skips allocating the SGM scratch: census, path volumes, WTA images) */
+    int enable_sgm;
     int min_disparity;    /* 4 */
     int num_disparities;  /* 64, 128 or 256 */
     int p1, p2;           /* 10, 120 */

@@ -1,0 +1,53 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY.  Builds oracle/_ref/libref.so: the REFERENCE'S OWN kernels for the non-SGM
+# stages, compiled for sm_100a straight from the sources where they lie under /root/reference
+# (line ranges per SURVEY.md Appendix E) behind a type shim, plus our host harness (*.inc).
+# The assembled translation units live in a temporary directory and are deleted; only the shared
+# library lands in oracle/_ref/ (git-ignored, ships to the GPU box).  The SGM stage cannot be built:
+# it is the third-party cv::cuda::StereoSGM (OpenCV-CUDA, absent here).
+set -euo pipefail
+R=${REFERENCE_ROOT:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT="$HERE/../_ref"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+[ -d "$R" ] || { echo "reference tree $R not present: keeping the prebuilt $OUT/libref.so"; exit 0; }
+mkdir -p "$OUT"
+if [ -f "$OUT/libref.so" ] && [ "$OUT/libref.so" -nt "$HERE/build_ref.sh" ] && [ "$OUT/libref.so" -nt "$HERE/shim.h" ] \
+   && [ -z "$(find "$HERE" -name '*.inc' -newer "$OUT/libref.so")" ]; then exit 0; fi
+T=$(mktemp -d)
+trap 'rm -rf "$T"' EXIT
+cut_() { sed -n "$2,$3p" "$R/$1"; }
+CU=include/utils/cuda.cuh
+SP=src/modules/superpixels/contourrelaxation
+SPI=include/modules/superpixels/contourrelaxation
+inc() { echo "#include \"$HERE/shim.h\""; }
+
+{ inc; cut_ $CU 10 15; echo "namespace cart {"; cut_ $CU 59 191; echo "}";
+  cut_ src/modules/disparity/derivative.cu 11 116; cat "$HERE/harness_derivative.inc"; } > "$T/derivative.cu"
+
+{ inc; cut_ $CU 10 15; cut_ $CU 31 36; echo "namespace cart {"; cut_ $CU 47 51; cut_ $CU 59 191;
+  cut_ include/modules/planeseg.hpp 25 41; echo "}"; echo "#define CARTSLAM_PLANE_COUNT 3";
+  cut_ src/modules/planeseg/planeseg.cu 11 243; cat "$HERE/harness_naive.inc"; } > "$T/naive.cu"
+
+{ inc; cut_ $CU 10 15; cut_ $CU 31 36; echo "namespace cart {"; cut_ $CU 47 51;
+  cut_ include/modules/planeseg.hpp 25 41; echo "}"; echo "#define CARTSLAM_PLANE_COUNT 3";
+  cut_ src/modules/planeseg/sp_planeseg.cu 12 21; cut_ src/modules/planeseg/sp_planeseg.cu 25 184;
+  cat "$HERE/harness_sp_planeseg.inc"; } > "$T/sp_planeseg.cu"
+
+{ inc; cut_ $CU 10 15; echo "namespace cart {"; cut_ $CU 59 191; echo "}";
+  cut_ src/modules/disparity/interpolation.cu 8 82; cat "$HERE/harness_interpolate.inc"; } > "$T/interpolate.cu"
+
+{ inc; cut_ $CU 10 15; cut_ $CU 25 27; echo "namespace cart {"; cut_ $CU 59 191; echo "}";
+  echo "namespace cart::contour { double const featuresMinVariance = 1.0 / 12.0;";
+  cut_ $SPI/features/ifeature.hpp 10 13; cut_ $SPI/features/feature.cuh 11 45; echo "}";
+  cut_ $SPI/features/gaussian.cuh 8 10; echo "namespace cart::contour {"; cut_ $SPI/features/gaussian.cuh 14 69;
+  cut_ $SP/features/gaussian.cu 5 21; cut_ $SP/features/gaussian.cu 30 206;
+  cut_ $SPI/features/compactness.cuh 28 58; cut_ $SP/features/compactness.cu 5 20; cut_ $SP/features/compactness.cu 28 197;
+  echo "}"; cut_ $SP/contourrelaxation.cu 10 327; cat "$HERE/harness_contour.inc"; } > "$T/contour.cu"
+
+FLAGS="-gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo --expt-relaxed-constexpr -Xcompiler -fPIC -w"
+for n in derivative naive sp_planeseg interpolate contour; do
+  $NVCC $FLAGS -c "$T/$n.cu" -o "$T/$n.o"
+done
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libref.so" "$T"/*.o -lcudart
+echo "built $OUT/libref.so"
