@@ -123,7 +123,7 @@ def cpu_arm(n_sample: int, L, R):
     try:
         import cv2
 
-        cv2.setNumThreads(0)
+        cv2.setNumThreads(-1)  # default: all host threads (0 would mean sequential)
         sg = cv2.StereoSGBM_create(minDisparity=MIN_DISP, numDisparities=D, blockSize=3, P1=10, P2=120,
                                    uniquenessRatio=12, mode=cv2.STEREO_SGBM_MODE_HH4)
         threads = cv2.getNumThreads()

@@ -52,6 +52,7 @@ namespace refh {
     } while (0)
 
 // pitched device image that mimics a cv::cuda::GpuMat allocation (cudaMallocPitch)
+constexpr int kSlackRows = 16;
 template <typename T>
 struct DevMat {
     T* data = nullptr;
@@ -61,15 +62,24 @@ struct DevMat {
         rows = r;
         cols = c;
         ch = channels;
-        return cudaMallocPitch((void**)&data, &step, (size_t)c * channels * sizeof(T), r) == cudaSuccess ? 0 : -1;
+        // kSlackRows zero-filled rows follow the image: the reference reads up to yPad rows past the last
+        // row; a real GpuMat allocation usually has mapped memory there, a tight one faults.
+        cudaError_t e = cudaMallocPitch((void**)&data, &step, (size_t)c * channels * sizeof(T), r + kSlackRows);
+        if (e == cudaSuccess) e = cudaMemset(data, 0, step * (size_t)(r + kSlackRows));
+        if (e != cudaSuccess) fprintf(stderr, "ref harness: cudaMallocPitch(%d x %d x %d) -> %s\n", r, c, channels, cudaGetErrorString(e));
+        return e == cudaSuccess ? 0 : -1;
     }
     int upload(const T* host) {
-        return cudaMemcpy2D(data, step, host, (size_t)cols * ch * sizeof(T), (size_t)cols * ch * sizeof(T), rows,
-                            cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
+        cudaError_t e = cudaMemcpy2D(data, step, host, (size_t)cols * ch * sizeof(T), (size_t)cols * ch * sizeof(T), rows,
+                                     cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) fprintf(stderr, "ref harness: upload -> %s\n", cudaGetErrorString(e));
+        return e == cudaSuccess ? 0 : -1;
     }
     int download(T* host) const {
-        return cudaMemcpy2D(host, (size_t)cols * ch * sizeof(T), data, step, (size_t)cols * ch * sizeof(T), rows,
-                            cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+        cudaError_t e = cudaMemcpy2D(host, (size_t)cols * ch * sizeof(T), data, step, (size_t)cols * ch * sizeof(T), rows,
+                                     cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) fprintf(stderr, "ref harness: download -> %s\n", cudaGetErrorString(e));
+        return e == cudaSuccess ? 0 : -1;
     }
     int zero() { return cudaMemset2D(data, step, 0, (size_t)cols * ch * sizeof(T), rows) == cudaSuccess ? 0 : -1; }
     cv::cuda::PtrStepSz<T> view() const { return cv::cuda::PtrStepSz<T>{data, step, cols, rows}; }

@@ -47,7 +47,12 @@ def main():
     smooth = po.interpolate(sgm, 2, 1, 64, W)  # canonical input for the next stages
     out["smooth_disparity"] = smooth
 
-    for tag, disp in (("smooth", smooth), ("noisy", noisy)):
+    # race-free inputs for the naive low-pass (the 5-tap vertical mean is the identity on them)
+    rows = np.ascontiguousarray(np.broadcast_to((np.arange(H)[:, None] * 3 + 70).astype(np.int16), (H, W)))
+    cols = np.ascontiguousarray(np.broadcast_to((np.arange(W)[None, :] * 2 + 70).astype(np.int16), (H, W)))
+    out["rows_disparity"], out["columns_disparity"] = rows, cols
+
+    for tag, disp in (("smooth", smooth), ("noisy", noisy), ("rows", rows), ("columns", cols)):
         deriv = np.zeros((H, W, 2), np.int16)
         hist = np.zeros((256, 2), np.int32)
         assert lib.ref_derivative(p(disp), W, H, p(deriv), p(hist), 5, C.byref(ms)) == 0
@@ -83,6 +88,11 @@ def main():
         assert f(p(lab), W, H, nlab, p(ycc), dv, its, 0.5, 0.5 / np.sqrt(2), kw["wc"], kw["pr"], kw["wd"], kw["wi"], C.byref(ms)) == 0
         out[name] = lab
         times[name] = ms.value
+        # run-to-run self-agreement of the reference (its stored feature costs race)
+        lab2 = lab0.copy()
+        assert f(p(lab2), W, H, nlab, p(ycc), dv, its, 0.5, 0.5 / np.sqrt(2), kw["wc"], kw["pr"], kw["wd"], kw["wi"], C.byref(ms)) == 0
+        out[name + "_rerun"] = lab2
+        times[name + "_self_agreement"] = float((lab == lab2).mean())
     # SP planeseg on the relaxed labels
     unsm = np.zeros((H, W), np.uint8)
     pls = np.zeros((H, W), np.uint8)
