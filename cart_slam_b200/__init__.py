@@ -78,6 +78,7 @@ def _load():
     lib.cartb200_disparity.argtypes = [vp, i, vp, vp, sz, sz, vp, sz, sz, vp]
     lib.cartb200_sgm_gray_census.argtypes = [vp, i, vp, vp, sz, sz, vp]
     lib.cartb200_sgm_aggregate.argtypes = [vp, i, vp]
+    lib.cartb200_sgm_aggregate_path.argtypes = [vp, i, i, vp]
     lib.cartb200_sgm_wta_post.argtypes = [vp, i, vp, sz, sz, vp]
     lib.cartb200_interpolate.argtypes = [vp, i, vp, sz, sz, i, i, i, i, vp]
     lib.cartb200_sgm_intermediate.argtypes = [vp, i, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
@@ -104,7 +105,7 @@ _lib = _load()
 EXPORTED_SYMBOLS = [
     "cartb200_default_config", "cartb200_create", "cartb200_destroy", "cartb200_last_error", "cartb200_version",
     "cartb200_launch_count", "cartb200_scratch_bytes", "cartb200_disparity", "cartb200_sgm_gray_census",
-    "cartb200_sgm_aggregate", "cartb200_sgm_wta_post", "cartb200_interpolate", "cartb200_sgm_intermediate",
+    "cartb200_sgm_aggregate", "cartb200_sgm_aggregate_path", "cartb200_sgm_wta_post", "cartb200_interpolate", "cartb200_sgm_intermediate",
     "cartb200_derivative", "cartb200_naive_derivative", "cartb200_classify", "cartb200_superpixels_reset",
     "cartb200_superpixels_relax", "cartb200_superpixels_set_labels", "cartb200_superpixels_border_map",
     "cartb200_sp_planeseg", "cartb200_histogram_peak_update", "cartb200_default_sequence_opts",
@@ -291,6 +292,9 @@ class Context:
 
     def sgm_aggregate(self, n):
         self._check(_lib.cartb200_sgm_aggregate(self._h, n, self._stream()))
+
+    def sgm_aggregate_path(self, n, path):
+        self._check(_lib.cartb200_sgm_aggregate_path(self._h, n, path, self._stream()))
 
     def sgm_wta_post(self, n):
         torch = self.torch

@@ -145,6 +145,10 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
         c->err = "paths must be 4 (MODE_HH4) or 8 (MODE_HH)";
         return fail(CARTB200_E_UNSUPPORTED);
     }
+    if (cfg->min_disparity < 0 || cfg->min_disparity > 1024) {
+        c->err = "min_disparity must be in 0..1024";
+        return fail(CARTB200_E_UNSUPPORTED);
+    }
     if (cfg->p1 < 0 || cfg->p2 < cfg->p1 || 31 + cfg->p2 > 255) {
         c->err = "need 0 <= p1 <= p2 and 31 + p2 <= 255 (u8 path volumes)";
         return fail(CARTB200_E_UNSUPPORTED);
@@ -164,7 +168,12 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
     const size_t W = c->W, H = c->H, B = c->B;
     int rc;
     c->grayPitch = alignUp(W, 128);
-    c->censusPitch = alignUp(W * 4, 128);
+    // census rows: D + 32 zero words in front (right-census reads reach D + 16 words left of column 0),
+    // min_disparity + 32 behind (16-word chunk loads run past the last column; the right census is stored
+    // shifted by min_disparity)
+    c->cenMargin = c->D + 32;
+    c->cenRowWords = alignUp((size_t)c->cenMargin + W + (size_t)std::max(0, cfg->min_disparity) + 32, 32);
+    c->censusPitch = c->cenRowWords * 4;
     c->dispPitch = alignUp(W * 2, 128);
     c->volFrameStride = H * W * (size_t)c->D;
     c->volPathStride = c->volFrameStride * B;
@@ -172,6 +181,10 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
         if ((rc = devAlloc(c, &c->grayL, B * H * c->grayPitch))) return fail(rc);
         if ((rc = devAlloc(c, &c->censusL, B * H * c->censusPitch))) return fail(rc);
         if ((rc = devAlloc(c, &c->censusR, B * H * c->censusPitch))) return fail(rc);
+        if (cudaMemset(c->censusL, 0, B * H * c->censusPitch) != cudaSuccess || cudaMemset(c->censusR, 0, B * H * c->censusPitch) != cudaSuccess) {
+            c->err = "cudaMemset failed";
+            return fail(CARTB200_E_CUDA);
+        }
         if ((rc = devAlloc(c, &c->volumes, c->volPathStride * c->P))) return fail(rc);
         if ((rc = devAlloc(c, &c->wtaL, B * H * c->dispPitch))) return fail(rc);
         if ((rc = devAlloc(c, &c->wtaR, B * H * c->dispPitch))) return fail(rc);
@@ -208,6 +221,8 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
         if ((rc = devAlloc(c, &c->spYcc, B * H * W * 4))) return fail(rc);
         if ((rc = devAlloc(c, &c->spStats, B * (size_t)(c->maxLabels + 1) * 24 * sizeof(double)))) return fail(rc);
         if ((rc = devAlloc(c, &c->spNew, B * H * W * sizeof(uint16_t)))) return fail(rc);
+        if ((rc = devAlloc(c, &c->spList, B * H * W * sizeof(uint32_t)))) return fail(rc);
+        if ((rc = devAlloc(c, &c->spCount, B * sizeof(int)))) return fail(rc);
         if ((rc = devAlloc(c, &c->votes, B * (size_t)c->maxLabels * 4 * sizeof(uint32_t)))) return fail(rc);
         if ((rc = launch_sp_reset(c, c->B, nullptr, nullptr))) return fail(rc);
         if (cudaDeviceSynchronize() != cudaSuccess) {
@@ -236,6 +251,8 @@ void cartb200_destroy(cartb200_ctx* c) {
     cudaFree(c->spYcc);
     cudaFree(c->spStats);
     cudaFree(c->spNew);
+    cudaFree(c->spList);
+    cudaFree(c->spCount);
     if (c->seq) {
         SeqScratch* q = static_cast<SeqScratch*>(c->seq);
         cudaFree(q->inL);
@@ -282,6 +299,17 @@ int cartb200_sgm_aggregate(cartb200_ctx* c, int n, void* stream) {
     return launch_aggregate(c, n, (cudaStream_t)stream);
 }
 
+int cartb200_sgm_aggregate_path(cartb200_ctx* c, int n, int path, void* stream) {
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    if ((rc = checkSgm(c))) return rc;
+    if (path < 0 || path >= c->P) {
+        c->err = "aggregate_path: path index out of range";
+        return CARTB200_E_ARG;
+    }
+    return launch_aggregate_range(c, n, path, path + 1, (cudaStream_t)stream);
+}
+
 int cartb200_interpolate(cartb200_ctx* c, int n, int16_t* d, size_t pitch, size_t fstride, int radius, int iterations,
                          int minD, int maxD, void* stream) {
     int rc = checkBatch(c, n);
@@ -326,8 +354,8 @@ int cartb200_sgm_intermediate(cartb200_ctx* c, int which, const void** ptr, size
     if (!c || !ptr || !pitch || !fstride) return CARTB200_E_ARG;
     const size_t H = c->H;
     switch (which) {
-        case 0: *ptr = c->censusL; *pitch = c->censusPitch; *fstride = c->censusPitch * H; return CARTB200_OK;
-        case 1: *ptr = c->censusR; *pitch = c->censusPitch; *fstride = c->censusPitch * H; return CARTB200_OK;
+        case 0: *ptr = c->censusL + c->cenMargin; *pitch = c->censusPitch; *fstride = c->censusPitch * H; return CARTB200_OK;
+        case 1: *ptr = c->censusR + c->cenMargin + c->cfg.min_disparity; *pitch = c->censusPitch; *fstride = c->censusPitch * H; return CARTB200_OK;
         case 2: *ptr = c->grayL; *pitch = c->grayPitch; *fstride = c->grayPitch * H; return CARTB200_OK;
         case 3: *ptr = c->wtaL; *pitch = c->dispPitch; *fstride = c->dispPitch * H; return CARTB200_OK;
         case 4: *ptr = c->wtaR; *pitch = c->dispPitch; *fstride = c->dispPitch * H; return CARTB200_OK;

@@ -52,7 +52,9 @@ struct cartb200_ctx {
     size_t grayPitch = 0;
     uint32_t* censusL = nullptr;  // [B][H][censusPitch/4]
     uint32_t* censusR = nullptr;
-    size_t censusPitch = 0;
+    size_t censusPitch = 0;      // bytes per census row = 4 * cenRowWords
+    size_t cenRowWords = 0;      // [cenMargin zeros][W words][zeros]
+    int cenMargin = 0;
     uint8_t* volumes = nullptr;  // [P][B][H][W][D]
     size_t volFrameStride = 0, volPathStride = 0;
     uint16_t* wtaL = nullptr;  // [B][H][dispPitch/2]
@@ -69,7 +71,9 @@ struct cartb200_ctx {
     size_t spLabelPitch = 0;
     uint8_t* spYcc = nullptr;  // [B][H][W][4] Y,Cr,Cb,border-flag scratch
     double* spStats = nullptr;     // [B][maxLabels][kStatDoubles]
-    uint16_t* spNew = nullptr;     // [B][H][W] decided labels (0xFFFF = not listed)
+    uint16_t* spNew = nullptr;     // [B][H*W] decided label per list entry
+    uint32_t* spList = nullptr;    // [B][H*W] listed border pixels (x | y << 16)
+    int* spCount = nullptr;        // [B] list lengths
     // sequence runner scratch (lazy)
     void* seq = nullptr;
 };
@@ -97,6 +101,7 @@ struct cartb200_ctx {
 namespace cb {
 int launch_gray_census(cartb200_ctx* c, int n, ImgBatch<const uint8_t> left, ImgBatch<const uint8_t> right, cudaStream_t s);
 int launch_aggregate(cartb200_ctx* c, int n, cudaStream_t s);
+int launch_aggregate_range(cartb200_ctx* c, int n, int p0, int p1, cudaStream_t s);
 int launch_wta(cartb200_ctx* c, int n, cudaStream_t s);
 int launch_sgm_post(cartb200_ctx* c, int n, ImgBatch<int16_t> disp, cudaStream_t s);
 int launch_interpolate(cartb200_ctx* c, int n, ImgBatch<int16_t> disp, int radius, int iterations, int minD, int maxD, cudaStream_t s);

@@ -20,7 +20,7 @@ constexpr int kCenTW = 120, kCenTH = 32;  // output tile; staged tile is (120+8)
 __global__ void __launch_bounds__(256) gray_census_kernel(ImgBatch<const uint8_t> left, ImgBatch<const uint8_t> right,
                                                           uint8_t* __restrict__ grayL, size_t grayPitch,
                                                           uint32_t* __restrict__ cenL, uint32_t* __restrict__ cenR,
-                                                          size_t cenPitch, int W, int H) {
+                                                          size_t cenRowWords, int cenMargin, int minDisp, int W, int H) {
     __shared__ uint8_t g[kCenTH + 6][kCenTW + 8];
     const int f = blockIdx.z >> 1, side = blockIdx.z & 1;
     Img<const uint8_t> src = side ? right.frame(f) : left.frame(f);
@@ -39,7 +39,10 @@ __global__ void __launch_bounds__(256) gray_census_kernel(ImgBatch<const uint8_t
         g[ty][tx] = v;
     }
     __syncthreads();
-    uint32_t* out = (side ? cenR : cenL) + (size_t)f * H * (cenPitch / 4);
+    // census rows carry zero margins (never written after create) so that the aggregation kernels can read
+    // out-of-image columns as the 0 the specification asks for; the RIGHT census is stored shifted by
+    // min_disparity: element (margin + i) holds cR[i - minDisp], i.e. the word for (x, d) is at x - d.
+    uint32_t* out = (side ? cenR : cenL) + (size_t)f * H * cenRowWords + cenMargin + (side ? minDisp : 0);
     for (int i = threadIdx.x; i < kCenTH * kCenTW; i += blockDim.x) {
         const int ty = i / kCenTW, tx = i % kCenTW;
         const int x = x0 + 4 + tx, y = y0 + 3 + ty;
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(256) gray_census_kernel(ImgBatch<const uint8_t
 #pragma unroll
             for (int dx = -4; dx < 0; ++dx) c = (c << 1) | (uint32_t)(g[cy][cx + dx] > g[cy][cx - dx]);
         }
-        out[(size_t)y * (cenPitch / 4) + x] = c;
+        out[(size_t)y * cenRowWords + x] = c;
     }
 }
 
@@ -62,56 +65,67 @@ int launch_gray_census(cartb200_ctx* c, int n, ImgBatch<const uint8_t> left, Img
                        cudaStream_t s) {
     dim3 grid(ceilDiv(c->W, kCenTW), ceilDiv(c->H, kCenTH), 2 * n);
     gray_census_kernel<<<grid, 256, 0, s>>>(left, right, c->grayL, c->grayPitch, c->censusL, c->censusR,
-                                            c->censusPitch, c->W, c->H);
+                                            c->cenRowWords, c->cenMargin, c->cfg.min_disparity, c->W, c->H);
     CB_LAUNCH_CHECK(c);
     return CARTB200_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Path aggregation (D3 + D4).  A group of LPP = D/16 lanes owns one path line; each lane carries 16
-// disparities as 8 x u16x2.  Per step: matching cost from the two census words, the recurrence
+// Path aggregation (D3 + D4).  A group of LPP = D/16 lanes owns one pixel's disparity vector; each
+// lane carries 16 disparities as 8 x u16x2.  Per pixel: matching cost from the two census words
+// (XOR + POPC - the POPC pipe, 16 lanes/clk/SM on B200, is the binding unit), the recurrence
 //   L(d) = C(d) + min(L'(d) - m, L'(d-1) - m + P1, L'(d+1) - m + P1, P2)
-// on packed halves, a min-reduction over the group by warp shuffles, one 16-byte store per lane
-// (a group writes the pixel's whole D-vector: full 128-B lines).
+// on packed halves (VIMNMX3.U16x2), a min-reduction over the group by warp shuffles and one 16-byte
+// store per lane (a group writes the pixel's whole D-vector: full 128-B lines).
+//   * horizontal paths: one group per image row; the right-census words a lane needs slide by one per
+//     step, so a 32-word register window is refilled with four 16-byte loads every 16 steps;
+//   * vertical paths: one group per FOUR adjacent columns (register blocking in x: 20 census words serve
+//     64 cells), five 16-byte loads per row;
+//   * diagonal paths (MODE_HH only): generic kernel, one group per path line.
 struct PathArgs {
-    const uint32_t* cenL;
-    const uint32_t* cenR;
+    const uint32_t* cenL;   // row layout: [margin zeros][W census words][zeros]; points at element 0 of row 0
+    const uint32_t* cenR;   // right census stored shifted by min_disparity (word for (x, d) at index x - d)
     size_t cenStride;       // words per row
     size_t cenFrameStride;  // words per frame
+    int cenMargin;          // words in front of column 0
     uint8_t* vol;           // this path's volume [B][H][W][D]
+    uint8_t* vol2;          // volume of the opposite direction when both are fused in one launch (blockIdx.z == 1)
     size_t volFrameStride;
-    int W, H, minDisp, P1, P2;
+    int W, H, P1, P2;
     int dx, dy;
 };
 
-__device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return lo | (hi << 16); }
+__device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return hi * 65536u + lo; }
 
 // One DP step for a lane's 16 disparities. dp[8] holds L' (previous pixel) on entry, L on exit.
-// prevHi = q of disparity (16*lane - 1), nextLo = q of disparity (16*lane + 16); both already minus m, or
-// the 0x7FFF sentinel at the ends of the disparity range.  cost[8] packed.  Returns the lane-local minimum.
-__device__ __forceinline__ uint32_t dp_step(uint32_t (&dp)[8], const uint32_t (&cost)[8], uint32_t M, uint32_t prevHi,
-                                            uint32_t nextLo, uint32_t P1v, uint32_t P2v) {
-    uint32_t q[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = dp[i] - M;  // halves are >= m: no borrow between them
-    uint32_t s[9];                                  // s[i] = (q[2i-1], q[2i])
-    s[0] = __byte_perm(prevHi, q[0], 0x5410);       // (prevHi.lo, q0.lo)
-#pragma unroll
-    for (int i = 1; i < 8; ++i) s[i] = __byte_perm(q[i - 1], q[i], 0x5432);
-    s[8] = __byte_perm(q[7], nextLo, 0x5432);
-    uint32_t mn = 0xFFFFFFFFu;
+// prevHiP = q(16*lane - 1) + P1 and nextLoP = q(16*lane + 16) + P1 (q = L' - m), or a large sentinel at the
+// ends of the disparity range.  Returns the lane-local minimum of the new L.
+__device__ __forceinline__ uint32_t dp_step(uint32_t (&dp)[8], const uint32_t (&cost)[8], uint32_t M, uint32_t prevHiP,
+                                            uint32_t nextLoP, uint32_t P1v, uint32_t P2v) {
+    uint32_t q[8], qp[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        // s[i]   = (q[2i-1], q[2i])   : the lower neighbour of each half
-        // s[i+1] = (q[2i+1], q[2i+2]) : the upper neighbour of each half
-        const uint32_t a = __viaddmin_u16x2(s[i], P1v, q[i]);     // min(q[d-1] + P1, q[d])
-        const uint32_t b = __viaddmin_u16x2(s[i + 1], P1v, P2v);  // min(q[d+1] + P1, P2)
-        const uint32_t r = __vminu2(a, b);
-        dp[i] = r + cost[i];
-        mn = __vminu2(mn, dp[i]);
+        q[i] = dp[i] - M;  // halves are >= m: no borrow between them
+        qp[i] = q[i] + P1v;
     }
+    uint32_t sp[9];  // sp[i] = (q[2i-1] + P1, q[2i] + P1): lower neighbours of reg i, upper neighbours of reg i-1
+    sp[0] = __byte_perm(prevHiP, qp[0], 0x5410);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) sp[i] = __byte_perm(qp[i - 1], qp[i], 0x5432);
+    sp[8] = __byte_perm(qp[7], nextLoP, 0x5432);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t qc = __vminu2(q[i], P2v);
+        dp[i] = __vimin3_u16x2(sp[i], sp[i + 1], qc) + cost[i];
+    }
+    uint32_t mn = __vimin3_u16x2(dp[0], dp[1], dp[2]);
+    mn = __vimin3_u16x2(mn, dp[3], dp[4]);
+    mn = __vimin3_u16x2(mn, dp[5], dp[6]);
+    mn = __vminu2(mn, dp[7]);
     return min(mn & 0xFFFFu, mn >> 16);
 }
+
+constexpr uint32_t kSentinel = 0x7FFFu;  // "no neighbour": larger than any q + P1, no u16 overflow
 
 template <int LPP>
 __device__ __forceinline__ uint32_t group_min(uint32_t v) {
@@ -120,18 +134,169 @@ __device__ __forceinline__ uint32_t group_min(uint32_t v) {
     return v;
 }
 
+// neighbours across lanes of a group: q(16*lane - 1) + P1 and q(16*lane + 16) + P1
+template <int LPP>
+__device__ __forceinline__ void lane_neighbours(const uint32_t (&dp)[8], uint32_t M, uint32_t P1, int lane, uint32_t& prevHiP,
+                                                uint32_t& nextLoP) {
+    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, dp[7], 1);
+    const uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, dp[0], 1);
+    prevHiP = lane == 0 ? kSentinel : (((up - M) >> 16) + P1);
+    nextLoP = lane == LPP - 1 ? kSentinel : (((dn - M) & 0xFFFFu) + P1);
+}
+
 __device__ __forceinline__ void store_dp(uint8_t* dst, const uint32_t (&dp)[8]) {
     uint4 o;
     o.x = __byte_perm(dp[0], dp[1], 0x6420);
     o.y = __byte_perm(dp[2], dp[3], 0x6420);
     o.z = __byte_perm(dp[4], dp[5], 0x6420);
     o.w = __byte_perm(dp[6], dp[7], 0x6420);
-    *reinterpret_cast<uint4*>(dst) = o;
+    __stcs(reinterpret_cast<uint4*>(dst), o);  // streaming store: the volume is not re-read before the WTA pass
 }
 
-// Generic kernel: any of the 8 directions.  Horizontal lines keep the 16 right-census words in a
-// register window that slides by one word per step; other directions fetch them per step (L1-resident).
-template <int D, int DXT>  // DXT: +1 / -1 horizontal specialisation, 0 = generic
+__device__ __forceinline__ void load16(uint32_t* dst, const uint32_t* src) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + k);
+        dst[4 * k] = v.x;
+        dst[4 * k + 1] = v.y;
+        dst[4 * k + 2] = v.z;
+        dst[4 * k + 3] = v.w;
+    }
+}
+
+// ---- horizontal -----------------------------------------------------------------------------------
+template <int D, int DX>
+__device__ __forceinline__ void horizontal_body(const PathArgs& a, uint8_t* __restrict__ volBase) {
+    constexpr int LPP = D / 16;
+    constexpr int GPB = 128 / LPP;
+    const int lane = threadIdx.x % LPP;
+    const int group = threadIdx.x / LPP;
+    const int f = blockIdx.y;
+    const int W = a.W;
+    const int line = blockIdx.x * GPB + group;
+    const bool valid = line < a.H;
+    const int y = valid ? line : a.H - 1;
+    const uint32_t* cl = a.cenL + (size_t)f * a.cenFrameStride + (size_t)y * a.cenStride + a.cenMargin;
+    const uint32_t* cr = a.cenR + (size_t)f * a.cenFrameStride + (size_t)y * a.cenStride + a.cenMargin - 16 * lane - 16;
+    uint8_t* vrow = volBase + (size_t)f * a.volFrameStride + (size_t)y * W * D + 16 * lane;
+    const uint32_t P1v = pack16(a.P1, a.P1), P2v = pack16(a.P2, a.P2);
+    const int nChunks = (W + 15) >> 4;
+
+    uint32_t dp[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dp[i] = 0;
+    uint32_t m = 0;
+    // S[k] = shifted right census word (x0 - 16*lane - 16 + k) of the current 16-pixel chunk starting at x0
+    uint32_t S[32];
+    {
+        const int x0 = DX > 0 ? 0 : 16 * (nChunks - 1);
+        load16(DX > 0 ? S : S + 16, cr + x0 + (DX > 0 ? 0 : 16));
+    }
+    for (int c = 0; c < nChunks; ++c) {
+        const int x0 = DX > 0 ? 16 * c : 16 * (nChunks - 1 - c);
+        uint32_t Lw[16];
+        load16(Lw, cl + x0);
+        load16(DX > 0 ? S + 16 : S, cr + x0 + (DX > 0 ? 16 : 0));
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int sidx = DX > 0 ? t : 15 - t;
+            const int x = x0 + sidx;
+            if (x < W) {  // warp-uniform: every group of the warp is at the same column
+                uint32_t cost[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    cost[i] = pack16(__popc(Lw[sidx] ^ S[16 + sidx - 2 * i]), __popc(Lw[sidx] ^ S[16 + sidx - 2 * i - 1]));
+                const uint32_t M = pack16(m, m);
+                uint32_t prevHiP, nextLoP;
+                lane_neighbours<LPP>(dp, M, a.P1, lane, prevHiP, nextLoP);
+                m = group_min<LPP>(dp_step(dp, cost, M, prevHiP, nextLoP, P1v, P2v));
+                if (valid) store_dp(vrow + (size_t)x * D, dp);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (DX > 0)
+                S[k] = S[k + 16];
+            else
+                S[k + 16] = S[k];
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) aggregate_horizontal_kernel(PathArgs a, int dirFirst, int both) {
+    // blockIdx.z selects the direction when both are fused in one launch
+    const int dir = both ? (blockIdx.z == 0 ? 1 : -1) : dirFirst;
+    uint8_t* vol = (both && blockIdx.z == 1) ? a.vol2 : a.vol;
+    if (dir > 0)
+        horizontal_body<D, 1>(a, vol);
+    else
+        horizontal_body<D, -1>(a, vol);
+}
+
+// ---- vertical -------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) aggregate_vertical_kernel(PathArgs a, int dirFirst, int both) {
+    constexpr int LPP = D / 16;
+    constexpr int GPB = 128 / LPP;
+    const int dir = both ? (blockIdx.z == 0 ? 1 : -1) : dirFirst;
+    uint8_t* volBase = (both && blockIdx.z == 1) ? a.vol2 : a.vol;
+    const int lane = threadIdx.x % LPP;
+    const int group = threadIdx.x / LPP;
+    const int f = blockIdx.y;
+    const int W = a.W, H = a.H;
+    const int nQuads = (W + 3) >> 2;
+    int quad = blockIdx.x * GPB + group;
+    const bool valid = quad < nQuads;
+    if (!valid) quad = nQuads - 1;
+    const int x0 = 4 * quad;
+    const uint32_t* clBase = a.cenL + (size_t)f * a.cenFrameStride + a.cenMargin + x0;
+    const uint32_t* crBase = a.cenR + (size_t)f * a.cenFrameStride + a.cenMargin + x0 - 16 * lane - 16;
+    uint8_t* vbase = volBase + (size_t)f * a.volFrameStride + (size_t)x0 * D + 16 * lane;
+    const uint32_t P1v = pack16(a.P1, a.P1), P2v = pack16(a.P2, a.P2);
+
+    uint32_t dp[4][8];
+    uint32_t m[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        m[c] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dp[c][i] = 0;
+    }
+    for (int step = 0; step < H; ++step) {
+        const int y = dir > 0 ? step : H - 1 - step;
+        const uint4 lw = __ldg(reinterpret_cast<const uint4*>(clBase + (size_t)y * a.cenStride));
+        const uint32_t Lw[4] = {lw.x, lw.y, lw.z, lw.w};
+        // S[k] = shifted right census word (x0 - 16*lane - 16 + k), k = 0..19; cell (x0+c, j) uses S[16 + c - j]
+        uint32_t S[20];
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(crBase + (size_t)y * a.cenStride);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const uint4 v = __ldg(src + k);
+                S[4 * k] = v.x;
+                S[4 * k + 1] = v.y;
+                S[4 * k + 2] = v.z;
+                S[4 * k + 3] = v.w;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t cost[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                cost[i] = pack16(__popc(Lw[c] ^ S[16 + c - 2 * i]), __popc(Lw[c] ^ S[16 + c - 2 * i - 1]));
+            const uint32_t M = pack16(m[c], m[c]);
+            uint32_t prevHiP, nextLoP;
+            lane_neighbours<LPP>(dp[c], M, a.P1, lane, prevHiP, nextLoP);
+            m[c] = group_min<LPP>(dp_step(dp[c], cost, M, prevHiP, nextLoP, P1v, P2v));
+            if (valid && x0 + c < W) store_dp(vbase + ((size_t)y * W + c) * D, dp[c]);
+        }
+    }
+}
+
+// ---- generic (diagonals) --------------------------------------------------------------------------
+template <int D>
 __global__ void __launch_bounds__(128) aggregate_path_kernel(PathArgs a) {
     constexpr int LPP = D / 16;
     constexpr int GPB = 128 / LPP;  // groups per block
@@ -139,7 +304,7 @@ __global__ void __launch_bounds__(128) aggregate_path_kernel(PathArgs a) {
     const int group = threadIdx.x / LPP;
     const int f = blockIdx.y;
     const int W = a.W, H = a.H;
-    const int dx = DXT != 0 ? DXT : a.dx, dy = DXT != 0 ? 0 : a.dy;
+    const int dx = a.dx, dy = a.dy;
     const int line = blockIdx.x * GPB + group;
     int nLines;
     if (dy == 0)
@@ -173,67 +338,34 @@ __global__ void __launch_bounds__(128) aggregate_path_kernel(PathArgs a) {
         const int lx = dx > 0 ? W - x : x + 1, ly = dy > 0 ? H - y : y + 1;
         len = min(lx, ly);
     }
-    // steps must be warp-uniform for the shuffles
-    int maxLen = len;
+    int maxLen = len;  // steps must be warp-uniform for the shuffles
 #pragma unroll
     for (int o = LPP; o < 32; o <<= 1) maxLen = max(maxLen, __shfl_xor_sync(0xFFFFFFFFu, maxLen, o));
 
-    const uint32_t* cl = a.cenL + (size_t)f * a.cenFrameStride;
-    const uint32_t* cr = a.cenR + (size_t)f * a.cenFrameStride;
+    const uint32_t* cl = a.cenL + (size_t)f * a.cenFrameStride + a.cenMargin;
+    const uint32_t* cr = a.cenR + (size_t)f * a.cenFrameStride + a.cenMargin - 16 * lane;
     uint8_t* vol = a.vol + (size_t)f * a.volFrameStride;
     const uint32_t P1v = pack16(a.P1, a.P1), P2v = pack16(a.P2, a.P2);
-    const int dbase = 16 * lane + a.minDisp;
-
     uint32_t dp[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dp[i] = 0;
     uint32_t m = 0;
-    uint32_t w[16];
-    if (DXT != 0) {
-        // window for the position BEFORE the first step (so the first step's shift brings it in place)
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int xr = (x - dx) - dbase - j;
-            w[j] = (len > 0 && xr >= 0 && xr < W) ? __ldg(cr + (size_t)y * a.cenStride + xr) : 0u;
-        }
-    }
     for (int step = 0; step < maxLen; ++step) {
         const bool act = step < len;
         uint32_t cost[8];
         if (act) {
-            const uint32_t* crow = cr + (size_t)y * a.cenStride;
             const uint32_t l = __ldg(cl + (size_t)y * a.cenStride + x);
-            if (DXT > 0) {
+            const uint32_t* crow = cr + (size_t)y * a.cenStride + x;  // margins make every index valid
 #pragma unroll
-                for (int j = 15; j > 0; --j) w[j] = w[j - 1];
-                const int xr = x - dbase;
-                w[0] = (xr >= 0 && xr < W) ? __ldg(crow + xr) : 0u;
-            } else if (DXT < 0) {
-#pragma unroll
-                for (int j = 0; j < 15; ++j) w[j] = w[j + 1];
-                const int xr = x - dbase - 15;
-                w[15] = (xr >= 0 && xr < W) ? __ldg(crow + xr) : 0u;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int xr = x - dbase - j;
-                    w[j] = (xr >= 0 && xr < W) ? __ldg(crow + xr) : 0u;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cost[i] = pack16(__popc(l ^ w[2 * i]), __popc(l ^ w[2 * i + 1]));
+            for (int i = 0; i < 8; ++i) cost[i] = pack16(__popc(l ^ __ldg(crow - 2 * i)), __popc(l ^ __ldg(crow - 2 * i - 1)));
         } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) cost[i] = 0;
         }
         const uint32_t M = pack16(m, m);
-        // neighbours across lanes (q = dp - m), sentinel at the ends of the disparity range
-        uint32_t up = __shfl_up_sync(0xFFFFFFFFu, dp[7], 1);
-        uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, dp[0], 1);
-        const uint32_t prevHi = lane == 0 ? 0x7FFFu : ((up - M) >> 16);
-        const uint32_t nextLo = lane == LPP - 1 ? 0x7FFFu : ((dn - M) & 0xFFFFu);
-        uint32_t lm = dp_step(dp, cost, M, prevHi, nextLo, P1v, P2v);
-        lm = group_min<LPP>(lm);
+        uint32_t prevHiP, nextLoP;
+        lane_neighbours<LPP>(dp, M, a.P1, lane, prevHiP, nextLoP);
+        const uint32_t lm = group_min<LPP>(dp_step(dp, cost, M, prevHiP, nextLoP, P1v, P2v));
         if (act) {
             m = lm;
             store_dp(vol + ((size_t)y * W + x) * D + 16 * lane, dp);
@@ -243,44 +375,61 @@ __global__ void __launch_bounds__(128) aggregate_path_kernel(PathArgs a) {
     }
 }
 
-template <int D>
-static void launch_path_D(const PathArgs& a, int n, cudaStream_t s) {
-    constexpr int GPB = 128 / (D / 16);
-    int nLines = a.dy == 0 ? a.H : (a.dx == 0 ? a.W : a.W + a.H - 1);
-    dim3 grid(ceilDiv(nLines, GPB), n);
-    if (a.dy == 0 && a.dx > 0)
-        aggregate_path_kernel<D, 1><<<grid, 128, 0, s>>>(a);
-    else if (a.dy == 0 && a.dx < 0)
-        aggregate_path_kernel<D, -1><<<grid, 128, 0, s>>>(a);
-    else
-        aggregate_path_kernel<D, 0><<<grid, 128, 0, s>>>(a);
-}
-
 static const int kDirs[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}};
 
-int launch_aggregate(cartb200_ctx* c, int n, cudaStream_t s) {
-    for (int p = 0; p < c->P; ++p) {
-        PathArgs a;
-        a.cenL = c->censusL;
-        a.cenR = c->censusR;
-        a.cenStride = c->censusPitch / 4;
-        a.cenFrameStride = a.cenStride * c->H;
+template <int D>
+static void launch_paths_D(cartb200_ctx* c, PathArgs a, int n, int p0, int p1, cudaStream_t s) {
+    constexpr int GPB = 128 / (D / 16);
+    for (int p = p0; p < p1; ++p) {
         a.vol = c->volumes + (size_t)p * c->volPathStride;
-        a.volFrameStride = c->volFrameStride;
-        a.W = c->W;
-        a.H = c->H;
-        a.minDisp = c->cfg.min_disparity;
-        a.P1 = c->cfg.p1;
-        a.P2 = c->cfg.p2;
         a.dx = kDirs[p][0];
         a.dy = kDirs[p][1];
-        switch (c->D) {
-            case 64: launch_path_D<64>(a, n, s); break;
-            case 128: launch_path_D<128>(a, n, s); break;
-            case 256: launch_path_D<256>(a, n, s); break;
-            default: c->err = "num_disparities must be 64, 128 or 256"; return CARTB200_E_UNSUPPORTED;
+        // opposite directions of an axis-aligned pair share one launch (twice the resident warps)
+        const bool pair = (p == 0 || p == 2) && p + 1 < p1;
+        a.vol2 = pair ? c->volumes + (size_t)(p + 1) * c->volPathStride : nullptr;
+        if (a.dy == 0) {
+            dim3 grid(ceilDiv(a.H, GPB), n, pair ? 2 : 1);
+            aggregate_horizontal_kernel<D><<<grid, 128, 0, s>>>(a, a.dx, pair ? 1 : 0);
+        } else if (a.dx == 0) {
+            dim3 grid(ceilDiv(ceilDiv(a.W, 4), GPB), n, pair ? 2 : 1);
+            aggregate_vertical_kernel<D><<<grid, 128, 0, s>>>(a, a.dy, pair ? 1 : 0);
+        } else {
+            dim3 grid(ceilDiv(a.W + a.H - 1, GPB), n);
+            aggregate_path_kernel<D><<<grid, 128, 0, s>>>(a);
         }
-        CB_LAUNCH_CHECK(c);
+        c->launches++;
+        if (pair) ++p;
+    }
+}
+
+int launch_aggregate_range(cartb200_ctx* c, int n, int p0, int p1, cudaStream_t s);
+
+int launch_aggregate(cartb200_ctx* c, int n, cudaStream_t s) { return launch_aggregate_range(c, n, 0, c->P, s); }
+
+int launch_aggregate_range(cartb200_ctx* c, int n, int p0, int p1, cudaStream_t s) {
+    PathArgs a;
+    a.cenL = c->censusL;
+    a.cenR = c->censusR;
+    a.cenStride = c->cenRowWords;
+    a.cenFrameStride = c->cenRowWords * c->H;
+    a.cenMargin = c->cenMargin;
+    a.vol = a.vol2 = nullptr;
+    a.volFrameStride = c->volFrameStride;
+    a.W = c->W;
+    a.H = c->H;
+    a.P1 = c->cfg.p1;
+    a.P2 = c->cfg.p2;
+    a.dx = a.dy = 0;
+    switch (c->D) {
+        case 64: launch_paths_D<64>(c, a, n, p0, p1, s); break;
+        case 128: launch_paths_D<128>(c, a, n, p0, p1, s); break;
+        case 256: launch_paths_D<256>(c, a, n, p0, p1, s); break;
+        default: c->err = "num_disparities must be 64, 128 or 256"; return CARTB200_E_UNSUPPORTED;
+    }
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        c->err = std::string("aggregate launch: ") + cudaGetErrorString(e);
+        return CARTB200_E_CUDA;
     }
     return CARTB200_OK;
 }

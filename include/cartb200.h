@@ -93,6 +93,8 @@ int cartb200_disparity(cartb200_ctx* ctx, int n, const uint8_t* left_bgr, const 
 int cartb200_sgm_gray_census(cartb200_ctx* ctx, int n, const uint8_t* left_bgr, const uint8_t* right_bgr,
                              size_t bgr_pitch, size_t bgr_frame_stride, void* stream);
 int cartb200_sgm_aggregate(cartb200_ctx* ctx, int n, void* stream);
+/* One path only (0 L->R, 1 R->L, 2 T->B, 3 B->T, 4..7 diagonals) - for per-kernel timing and parity tests. */
+int cartb200_sgm_aggregate_path(cartb200_ctx* ctx, int n, int path, void* stream);
 int cartb200_sgm_wta_post(cartb200_ctx* ctx, int n, int16_t* disparity, size_t disp_pitch, size_t disp_frame_stride,
                           void* stream);
 /* In-place smoothing of an existing CV_16SC1 image (interpolation.cu:85-99). min_disparity is the
