@@ -35,7 +35,14 @@ def main():
     ap.add_argument("--height", type=int, default=375)
     ap.add_argument("--disp", type=int, default=128)
     ap.add_argument("--block", type=int, default=12)
+    ap.add_argument("--once", action="store_true", help="run every stage exactly once (for ncu captures)")
     args = ap.parse_args()
+    if args.once:
+        global timeit
+        def timeit(fn, reps=1, warm=0):  # noqa: F811
+            fn()
+            torch.cuda.synchronize()
+            return 1e-6
     W, H, D, B = args.width, args.height, args.disp, args.batch
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     seq = SyntheticSequence(W, H, D, n_frames=4, tint=True)
@@ -49,7 +56,7 @@ def main():
         res["gray_census"] = timeit(lambda: ctx.sgm_gray_census(L, R))
         for p in range(args.paths):
             res[f"aggregate_path{p}"] = timeit(lambda: ctx.sgm_aggregate_path(B, p))
-        ctx.sgm_aggregate(B)
+        res["aggregate_all_paths"] = timeit(lambda: ctx.sgm_aggregate(B))
         res["wta_post_interp"] = timeit(lambda: ctx.sgm_wta_post(B))
         disp = ctx.sgm_wta_post(B)
         res["derivative"] = timeit(lambda: ctx.derivative(disp))
@@ -57,7 +64,7 @@ def main():
         deriv, _ = ctx.derivative(disp)
         ctx.superpixels_reset(B)
         r0 = timeit(lambda: ctx.superpixels_relax(L, deriv, 0), reps=5)
-        r8 = timeit(lambda: ctx.superpixels_relax(L, deriv, 8), reps=5)
+        r8 = timeit(lambda: ctx.superpixels_relax(L, deriv, 2 if args.once else 8), reps=5)
         res["sp_relax_0it"] = r0
         res["sp_relax_per_iteration"] = (r8 - r0) / 8
         labels = ctx.superpixels_relax(L, deriv, 8)
@@ -68,6 +75,9 @@ def main():
         extra = ""
         if k.startswith("aggregate_path"):
             gbs = (vol_bytes + B * 2 * 4 * W * H) / (v * 1e-3) / 1e9
+            extra = f"  {gbs:7.0f} GB/s  {gbs / peak:5.3f}"
+        if k == "aggregate_all_paths":
+            gbs = args.paths * (vol_bytes + B * 2 * 4 * W * H) / (v * 1e-3) / 1e9
             extra = f"  {gbs:7.0f} GB/s  {gbs / peak:5.3f}"
         if k == "wta_post_interp":
             gbs = (args.paths * vol_bytes) / (v * 1e-3) / 1e9
