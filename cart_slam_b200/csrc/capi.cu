@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -10,6 +11,7 @@
 
 namespace cb {
 uint32_t debug_median9_host(const uint16_t* v9);
+int launch_right_u16(cartb200_ctx* c, int n, uint16_t* out, cudaStream_t s);
 int histogram_peak_update(const int32_t* hist, int32_t* params);  // plane_params.cpp
 }  // namespace cb
 
@@ -58,6 +60,33 @@ int ensureCap(cartb200_ctx* c, T** p, size_t* cap, size_t bytes) {
     if (rc == CARTB200_OK) *cap = bytes;
     return rc;
 }
+
+}  // namespace
+
+namespace cb {
+// WTA + medians / L-R check / range correction + (smoothing_radius > 0) the interpolation pass
+int wta_post_batch(cartb200_ctx* c, int n, ImgBatch<int16_t> out, cudaStream_t s) {
+    int rc;
+    if ((rc = launch_wta(c, n, s))) return rc;
+    if (c->cfg.smoothing_radius <= 0) return launch_sgm_post(c, n, out, s);
+    // the raw disparity goes to the staging image; the smoothing pass reads it out of place
+    ImgBatch<int16_t> tmp{(int16_t*)c->medL, c->dispPitch, c->dispPitch * (size_t)c->H};
+    if ((rc = launch_sgm_post(c, n, tmp, s))) return rc;
+    // ImageDisparityModule passes minDisparity*16 and the image width (disparity.hpp:27-28, disparity.cu:74)
+    return launch_interpolate_from(c, n, ImgBatch<const int16_t>{tmp.data, tmp.pitch, tmp.frameStride}, out,
+                                   c->cfg.smoothing_radius, c->cfg.smoothing_iterations, c->cfg.min_disparity * 16, c->W, s);
+}
+
+int disparity_batch(cartb200_ctx* c, int n, ImgBatch<const uint8_t> left, ImgBatch<const uint8_t> right, ImgBatch<int16_t> disp,
+                    cudaStream_t s) {
+    int rc;
+    if ((rc = launch_gray_census(c, n, left, right, s))) return rc;
+    if ((rc = launch_aggregate(c, n, s))) return rc;
+    return wta_post_batch(c, n, disp, s);
+}
+}  // namespace cb
+
+namespace {
 
 int* slotIota(cartb200_ctx* c) { return reinterpret_cast<int*>(c->paramsDev + 4 * (size_t)c->B); }
 int* slotScratch(cartb200_ctx* c) { return slotIota(c) + c->B; }
@@ -187,7 +216,8 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
         }
         if ((rc = devAlloc(c, &c->volumes, c->volPathStride * c->P))) return fail(rc);
         if ((rc = devAlloc(c, &c->wtaL, B * H * c->dispPitch))) return fail(rc);
-        if ((rc = devAlloc(c, &c->wtaR, B * H * c->dispPitch))) return fail(rc);
+        c->rkPitch = alignUp(W, 32);
+        if ((rc = devAlloc(c, &c->wtaR, B * H * c->rkPitch * sizeof(uint32_t)))) return fail(rc);
     }
     if ((rc = devAlloc(c, &c->medL, B * H * c->dispPitch))) return fail(rc);  // also the interpolation staging image
     // paramsDev [B][4] + slot iota [B] + slot scratch [B]
@@ -330,16 +360,7 @@ int cartb200_sgm_wta_post(cartb200_ctx* c, int n, int16_t* d, size_t pitch, size
         c->err = "wta_post: bad image arguments";
         return CARTB200_E_ARG;
     }
-    cudaStream_t s = (cudaStream_t)stream;
-    if ((rc = launch_wta(c, n, s))) return rc;
-    ImgBatch<int16_t> out{d, pitch, fstride};
-    if ((rc = launch_sgm_post(c, n, out, s))) return rc;
-    if (c->cfg.smoothing_radius > 0) {
-        // ImageDisparityModule passes minDisparity*16 and the image width (disparity.hpp:27-28, disparity.cu:74)
-        rc = launch_interpolate(c, n, out, c->cfg.smoothing_radius, c->cfg.smoothing_iterations,
-                                c->cfg.min_disparity * 16, c->W, s);
-    }
-    return rc;
+    return cb::wta_post_batch(c, n, ImgBatch<int16_t>{d, pitch, fstride}, (cudaStream_t)stream);
 }
 
 int cartb200_disparity(cartb200_ctx* c, int n, const uint8_t* l, const uint8_t* r, size_t pitch, size_t fstride,
@@ -358,7 +379,13 @@ int cartb200_sgm_intermediate(cartb200_ctx* c, int which, const void** ptr, size
         case 1: *ptr = c->censusR + c->cenMargin + c->cfg.min_disparity; *pitch = c->censusPitch; *fstride = c->censusPitch * H; return CARTB200_OK;
         case 2: *ptr = c->grayL; *pitch = c->grayPitch; *fstride = c->grayPitch * H; return CARTB200_OK;
         case 3: *ptr = c->wtaL; *pitch = c->dispPitch; *fstride = c->dispPitch * H; return CARTB200_OK;
-        case 4: *ptr = c->wtaR; *pitch = c->dispPitch; *fstride = c->dispPitch * H; return CARTB200_OK;
+        case 4: {  // the right image is kept as u32 keys; hand out a u16 copy (synchronous, debug only)
+            if (!c->medR && devAlloc(c, &c->medR, (size_t)c->B * H * c->dispPitch)) return CARTB200_E_NOMEM;
+            int rc = launch_right_u16(c, c->B, c->medR, nullptr);
+            if (rc) return rc;
+            CB_CHECK_CUDA(c, cudaDeviceSynchronize());
+            *ptr = c->medR; *pitch = c->dispPitch; *fstride = c->dispPitch * H; return CARTB200_OK;
+        }
         default:
             if (which >= 10 && which < 10 + c->P) {
                 *ptr = c->volumes + (size_t)(which - 10) * c->volPathStride;
@@ -633,8 +660,9 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
     if (q->nFrames < n) {
         cudaFreeHost(q->histHost);
         cudaFreeHost(q->paramsHost);
-        CB_CHECK_CUDA(c, cudaMallocHost((void**)&q->histHost, (size_t)n * 512 * sizeof(int32_t)));
-        CB_CHECK_CUDA(c, cudaMallocHost((void**)&q->paramsHost, (size_t)n * 4 * sizeof(int32_t)));
+        const size_t cap = std::max<size_t>((size_t)n, B);
+        CB_CHECK_CUDA(c, cudaMallocHost((void**)&q->histHost, cap * 512 * sizeof(int32_t)));
+        CB_CHECK_CUDA(c, cudaMallocHost((void**)&q->paramsHost, cap * 4 * sizeof(int32_t)));
         q->nFrames = n;
     }
     uint8_t* planesDev = outputsOnHost ? q->planes : planesOut;
@@ -712,15 +740,19 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
     const int nChunks = k1 - k0 + 1;
     if (!peak) {  // static ranges are the same for every frame: upload them once
         for (size_t j = 0; j < B; ++j) std::memcpy(q->paramsHost + 4 * j, hs.params + 2, 4 * sizeof(int32_t));
-        if ((rc = uploadParams(c, (int)std::min<size_t>(B, (size_t)n), q->paramsHost, s))) return rc;
+        if ((rc = uploadParams(c, (int)B, q->paramsHost, s))) return rc;
     }
     // a sequence that starts at id 1 starts from the constructor's block initialisation (superpixels.cu:56-58)
     if (firstId == 1 && (rc = launch_sp_reset(c, 1, slotIota(c), s))) return rc;
-    for (int g0 = 0; g0 < nChunks; g0 += (int)B) {  // groups of at most B chunks (one slot per chunk)
-        const int gN = std::min<int>((int)B, nChunks - g0);
-        for (int st = 0; st < R; ++st) {
-            // chunks of this group that own a frame at this step form a contiguous range [ca, cb)
-            int ca = -1, cb = -1;
+    // Chunks are grouped so that every chunk of a group owns one superpixel slot.  The SGM/derivative stages
+    // have no frame-to-frame state, so they run on up to B frames at once: `nb` chunks x `k` consecutive
+    // steps (two-level ImgBatch); only the superpixel relaxation advances step by step.
+    const int maxSlots = (int)B;
+    for (int g0 = 0; g0 < nChunks; g0 += maxSlots) {
+        const int gN = std::min<int>(maxSlots, nChunks - g0);
+        const int K = std::max<int>(1, (int)B / gN);
+        auto range = [&](int st, int& ca, int& cb) {  // chunks of this group that own a frame at step st
+            ca = cb = -1;
             for (int j = 0; j < gN; ++j) {
                 const int id = (k0 + g0 + j) * R + st;
                 if (id >= firstId && id <= lastId && id >= 1) {
@@ -728,61 +760,84 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
                     cb = j + 1;
                 }
             }
-            if (ca < 0) continue;
-            const int nb = cb - ca;
-            const int idA = (k0 + g0 + ca) * R + st;
-            const size_t fiA = (size_t)(idA - firstId);            // frame index of the first chunk in the batch
-            const size_t fStride = (size_t)R;                      // frames between consecutive chunks
-            const int* slots = slotIota(c) + ca;
-            const uint8_t* bl = devL + bgrFrame * fiA;
-            const uint8_t* br = devR + bgrFrame * fiA;
-            // disparity
-            int16_t* dB = dispOut ? dispDev + pxFrame * fiA : dispDev;
-            const size_t dStride = dispOut ? pxFrame * 2 * fStride : pxFrame * 2;
-            if ((rc = cartb200_disparity(c, nb, bl, br, W * 3, bgrFrame * fStride, dB, W * 2, dStride, s))) return rc;
-            // derivative + per-frame histogram
-            int16_t* vB = (peak ? q->deriv + pxFrame * 2 * fiA : q->deriv);
-            const size_t vStride = peak ? pxFrame * 4 * fStride : pxFrame * 4;
-            // histograms are stored batch-contiguously in a staging area and scattered on the host
-            if ((rc = launch_derivative(c, nb, ImgBatch<const int16_t>{dB, W * 2, dStride},
-                                        ImgBatch<int16_t>{vB, W * 4, vStride}, q->hist + 512 * (size_t)0, s)))
-                return rc;
-            // histogram rows for this batch land at q->hist[0..nb); move them to their frame slots
-            if (peak) {
-                for (int j = 0; j < nb; ++j)
-                    CB_CHECK_CUDA(c, cudaMemcpyAsync(q->histHost + 512 * (fiA + j * fStride), q->hist + 512 * (size_t)j,
-                                                     512 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        };
+        for (int st = 0; st < R;) {
+            int ca, cb;
+            range(st, ca, cb);
+            if (ca < 0) {
+                ++st;
+                continue;
             }
-            // superpixels: reset + iteration schedule (superpixels.cu:93-113)
-            const bool resetStep = st == 0;  // id % R == 0
-            if (resetStep && (rc = launch_sp_reset(c, nb, slots, s))) return rc;
-            uint16_t* lB = peak ? q->labels + pxFrame * fiA : q->labels;
-            const size_t lStride = peak ? pxFrame * 2 * fStride : pxFrame * 2;
-            const ImgBatch<const int16_t> dv{vB, W * 4, vStride};
-            // id == 1 also gets the initial iteration count (only chunk 0 at step 1 can be id 1)
-            if (!resetStep && idA == 1) {
-                if ((rc = launch_sp_relax(c, 1, slots, o->sp_initial_iterations, ImgBatch<const uint8_t>{bl, W * 3, bgrFrame * fStride},
-                                          dv, true, ImgBatch<uint16_t>{lB, W * 2, lStride}, s)))
-                    return rc;
-                if (nb > 1 &&
-                    (rc = launch_sp_relax(c, nb - 1, slots + 1, o->sp_iterations,
-                                          ImgBatch<const uint8_t>{bl + bgrFrame * fStride, W * 3, bgrFrame * fStride},
-                                          ImgBatch<const int16_t>{(const int16_t*)((const char*)vB + vStride), W * 4, vStride}, true,
-                                          ImgBatch<uint16_t>{(uint16_t*)((char*)lB + lStride), W * 2, lStride}, s)))
-                    return rc;
-            } else {
-                const int its = resetStep ? o->sp_initial_iterations : o->sp_iterations;
-                if ((rc = launch_sp_relax(c, nb, slots, its, ImgBatch<const uint8_t>{bl, W * 3, bgrFrame * fStride}, dv, true,
-                                          ImgBatch<uint16_t>{lB, W * 2, lStride}, s)))
-                    return rc;
+            int k = 1;
+            for (; st + k < R && k < K; ++k) {
+                int ca2, cb2;
+                range(st + k, ca2, cb2);
+                if (ca2 != ca || cb2 != cb) break;
+            }
+            const int nb = cb - ca, total = nb * k;
+            const int idA = (k0 + g0 + ca) * R + st;
+            const size_t fiA = (size_t)(idA - firstId);  // frame index of (first chunk, first step)
+            const size_t fStride = (size_t)R;            // frames between consecutive chunks
+            const int* slots = slotIota(c) + ca;
+            auto seqBatch = [&](auto* base, size_t frameBytes) {  // frames in sequence order, two-level
+                using T = std::remove_pointer_t<decltype(base)>;
+                return ImgBatch<T>{(T*)((char*)base + frameBytes * fiA), 0, frameBytes * fStride, nb, frameBytes};
+            };
+            ImgBatch<const uint8_t> bl = seqBatch(devL, bgrFrame), br = seqBatch(devR, bgrFrame);
+            bl.pitch = br.pitch = W * 3;
+            // disparity (all `total` frames)
+            ImgBatch<int16_t> dB = dispOut ? seqBatch(dispDev, pxFrame * 2) : ImgBatch<int16_t>{dispDev, 0, pxFrame * 2};
+            dB.pitch = W * 2;
+            if ((rc = disparity_batch(c, total, bl, br, dB, s))) return rc;
+            // derivative + per-frame histograms (staged batch-contiguously, scattered to their frame slots below)
+            ImgBatch<int16_t> vB = peak ? seqBatch(q->deriv, pxFrame * 4) : ImgBatch<int16_t>{q->deriv, 0, pxFrame * 4};
+            vB.pitch = W * 4;
+            const ImgBatch<const int16_t> dBc{dB.data, dB.pitch, dB.frameStride, dB.inner, dB.outerStride};
+            if ((rc = launch_derivative(c, total, dBc, vB, q->hist, s))) return rc;
+            if (peak) {
+                for (int kk = 0; kk < k; ++kk)
+                    for (int j = 0; j < nb; ++j)
+                        CB_CHECK_CUDA(c, cudaMemcpyAsync(q->histHost + 512 * (fiA + j * fStride + kk),
+                                                         q->hist + 512 * (size_t)(kk * nb + j), 512 * sizeof(int32_t),
+                                                         cudaMemcpyDeviceToHost, s));
+            }
+            ImgBatch<uint16_t> lB = peak ? seqBatch(q->labels, pxFrame * 2) : ImgBatch<uint16_t>{q->labels, 0, pxFrame * 2};
+            lB.pitch = W * 2;
+            ImgBatch<uint8_t> pB = seqBatch(planesDev, pxFrame);
+            pB.pitch = W;
+            // superpixels, one step at a time: reset + iteration schedule (superpixels.cu:93-113)
+            for (int kk = 0; kk < k; ++kk) {
+                auto step = [&](auto batch) {  // the nb frames of step st + kk as a simple strided batch
+                    using BT = decltype(batch);
+                    if (batch.inner > 0) return BT{(decltype(batch.data))((char*)batch.data + batch.outerStride * kk), batch.pitch, batch.frameStride};
+                    return BT{(decltype(batch.data))((char*)batch.data + batch.frameStride * (size_t)kk * nb), batch.pitch, batch.frameStride};
+                };
+                const bool resetStep = st + kk == 0;  // id % R == 0
+                if (resetStep && (rc = launch_sp_reset(c, nb, slots, s))) return rc;
+                const ImgBatch<const uint8_t> sl = step(bl);
+                const ImgBatch<int16_t> svm = step(vB);
+                const ImgBatch<const int16_t> sv{svm.data, svm.pitch, svm.frameStride};
+                const ImgBatch<uint16_t> so = step(lB);
+                // id == 1 also gets the initial iteration count (only chunk 0 at step 1 can be id 1)
+                if (!resetStep && idA + kk == 1) {
+                    if ((rc = launch_sp_relax(c, 1, slots, o->sp_initial_iterations, sl, sv, true, so, s))) return rc;
+                    if (nb > 1 && (rc = launch_sp_relax(c, nb - 1, slots + 1, o->sp_iterations, sl.from(1), sv.from(1), true,
+                                                        so.from(1), s)))
+                        return rc;
+                } else {
+                    const int its = resetStep ? o->sp_initial_iterations : o->sp_iterations;
+                    if ((rc = launch_sp_relax(c, nb, slots, its, sl, sv, true, so, s))) return rc;
+                }
             }
             if (!peak) {
-                // static ranges: vote + assign right away
-                if ((rc = launch_sp_planeseg(c, nb, dv, ImgBatch<const uint16_t>{lB, W * 2, lStride}, c->maxLabels,
-                                             c->paramsDev, ImgBatch<uint8_t>{q->unsm, W, pxFrame},
-                                             ImgBatch<uint8_t>{planesDev + pxFrame * fiA, W, pxFrame * fStride}, s)))
+                // static ranges: vote + assign right away (the same ranges for every frame of the batch)
+                const ImgBatch<const int16_t> vBc{vB.data, vB.pitch, vB.frameStride, vB.inner, vB.outerStride};
+                const ImgBatch<const uint16_t> lBc{lB.data, lB.pitch, lB.frameStride, lB.inner, lB.outerStride};
+                if ((rc = launch_sp_planeseg(c, total, vBc, lBc, c->maxLabels, c->paramsDev,
+                                             ImgBatch<uint8_t>{q->unsm, W, pxFrame}, pB, s)))
                     return rc;
             }
+            st += k;
         }
     }
     if (peak) {

@@ -22,11 +22,18 @@ struct Img {  // pitched device image view
 };
 
 template <typename T>
-struct ImgBatch {  // n frames with a constant byte stride
+struct ImgBatch {  // n frames with a constant byte stride; optionally a two-level layout (inner x outer)
     T* data;
     size_t pitch, frameStride;  // bytes
+    int inner = 0;              // > 0: frame f lives at (f % inner) * frameStride + (f / inner) * outerStride
+    size_t outerStride = 0;     //      (chunks x consecutive steps of a sequence processed in one launch)
     __host__ __device__ __forceinline__ Img<T> frame(int f) const {
-        return Img<T>{(T*)((char*)data + (size_t)f * frameStride), pitch};
+        const size_t off = inner > 0 ? (size_t)(f % inner) * frameStride + (size_t)(f / inner) * outerStride
+                                     : (size_t)f * frameStride;
+        return Img<T>{(T*)((char*)data + off), pitch};
+    }
+    __host__ __device__ __forceinline__ ImgBatch<T> from(int f0) const {  // sub-batch starting at simple-layout frame f0
+        return ImgBatch<T>{(T*)((char*)data + (size_t)f0 * frameStride), pitch, frameStride, inner, outerStride};
     }
 };
 
@@ -58,7 +65,8 @@ struct cartb200_ctx {
     uint8_t* volumes = nullptr;  // [P][B][H][W][D]
     size_t volFrameStride = 0, volPathStride = 0;
     uint16_t* wtaL = nullptr;  // [B][H][dispPitch/2]
-    uint16_t* wtaR = nullptr;
+    uint32_t* wtaR = nullptr;  // [B][H][rkPitch] right-image keys (aggregated cost << 16 | disparity)
+    size_t rkPitch = 0;        // elements
     uint16_t* medL = nullptr;
     uint16_t* medR = nullptr;
     size_t dispPitch = 0;
@@ -100,11 +108,13 @@ struct cartb200_ctx {
 // stage launchers (defined in the per-stage .cu files); all return CARTB200_* codes
 namespace cb {
 int launch_gray_census(cartb200_ctx* c, int n, ImgBatch<const uint8_t> left, ImgBatch<const uint8_t> right, cudaStream_t s);
+int disparity_batch(cartb200_ctx* c, int n, ImgBatch<const uint8_t> left, ImgBatch<const uint8_t> right, ImgBatch<int16_t> disp, cudaStream_t s);
 int launch_aggregate(cartb200_ctx* c, int n, cudaStream_t s);
 int launch_aggregate_range(cartb200_ctx* c, int n, int p0, int p1, cudaStream_t s);
 int launch_wta(cartb200_ctx* c, int n, cudaStream_t s);
 int launch_sgm_post(cartb200_ctx* c, int n, ImgBatch<int16_t> disp, cudaStream_t s);
 int launch_interpolate(cartb200_ctx* c, int n, ImgBatch<int16_t> disp, int radius, int iterations, int minD, int maxD, cudaStream_t s);
+int launch_interpolate_from(cartb200_ctx* c, int n, ImgBatch<const int16_t> src, ImgBatch<int16_t> dst, int radius, int iterations, int minD, int maxD, cudaStream_t s);
 int launch_derivative(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<int16_t> deriv, int32_t* hist, cudaStream_t s);
 int launch_naive_derivative(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<int16_t> deriv, int32_t* hist, cudaStream_t s);
 int launch_classify(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, int channels, int channel, const int32_t* paramsDev, ImgBatch<uint8_t> planes, cudaStream_t s);

@@ -71,21 +71,13 @@ __global__ void __launch_bounds__(256) interpolate_kernel(ImgBatch<const int16_t
     }
 }
 
-int launch_interpolate(cartb200_ctx* c, int n, ImgBatch<int16_t> disp, int radius, int iterations, int minD, int maxD,
-                       cudaStream_t s) {
-    if (radius <= 0) return CARTB200_OK;
+int launch_interpolate_from(cartb200_ctx* c, int n, ImgBatch<const int16_t> src, ImgBatch<int16_t> dst, int radius,
+                            int iterations, int minD, int maxD, cudaStream_t s) {
     const int pad = radius - 1, S = 64 + 2 * pad;
     const size_t smem = (size_t)2 * S * S * sizeof(int16_t);
     if (smem > 200 * 1024) {
         c->err = "interpolate: smoothing radius too large for shared memory";
         return CARTB200_E_UNSUPPORTED;
-    }
-    // stage the original image (canonical out-of-place read), medL is free at this point
-    ImgBatch<int16_t> tmp{(int16_t*)c->medL, c->dispPitch, c->dispPitch * (size_t)c->H};
-    for (int f = 0; f < n; ++f) {
-        Img<int16_t> a = disp.frame(f), b = tmp.frame(f);
-        CB_CHECK_CUDA(c, cudaMemcpy2DAsync(b.data, b.pitch, a.data, a.pitch, (size_t)c->W * 2, c->H,
-                                           cudaMemcpyDeviceToDevice, s));
     }
     static bool attr = false;
     if (!attr) {
@@ -93,10 +85,23 @@ int launch_interpolate(cartb200_ctx* c, int n, ImgBatch<int16_t> disp, int radiu
         attr = true;
     }
     dim3 grid(ceilDiv(c->W, 64), ceilDiv(c->H, 64), n);
-    ImgBatch<const int16_t> src{tmp.data, tmp.pitch, tmp.frameStride};
-    interpolate_kernel<<<grid, 256, smem, s>>>(src, disp, c->W, c->H, radius, iterations, minD, maxD);
+    interpolate_kernel<<<grid, 256, smem, s>>>(src, dst, c->W, c->H, radius, iterations, minD, maxD);
     CB_LAUNCH_CHECK(c);
     return CARTB200_OK;
+}
+
+int launch_interpolate(cartb200_ctx* c, int n, ImgBatch<int16_t> disp, int radius, int iterations, int minD, int maxD,
+                       cudaStream_t s) {
+    if (radius <= 0) return CARTB200_OK;
+    // stage the original image (canonical out-of-place read), medL is free at this point
+    ImgBatch<int16_t> tmp{(int16_t*)c->medL, c->dispPitch, c->dispPitch * (size_t)c->H};
+    for (int f = 0; f < n; ++f) {
+        Img<int16_t> a = disp.frame(f), b = tmp.frame(f);
+        CB_CHECK_CUDA(c, cudaMemcpy2DAsync(b.data, b.pitch, a.data, a.pitch, (size_t)c->W * 2, c->H,
+                                           cudaMemcpyDeviceToDevice, s));
+    }
+    return launch_interpolate_from(c, n, ImgBatch<const int16_t>{tmp.data, tmp.pitch, tmp.frameStride}, disp, radius,
+                                   iterations, minD, maxD, s);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -9,6 +9,8 @@
 // Arithmetic: path costs are <= 31 + P2 (u8 in memory); inside the kernels two disparities share a
 // register as u16x2 and the recurrence runs on the DPX/video integer instructions of sm_90+/sm_100
 // (VIADDMNMX.U16x2, VIMNMX.U16x2, VIMNMX3) - no tensor cores: nothing here is a dense contraction.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace cb {
@@ -97,25 +99,36 @@ struct PathArgs {
 
 __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return hi * 65536u + lo; }
 
-// One DP step for a lane's 16 disparities. dp[8] holds L' (previous pixel) on entry, L on exit.
-// prevHiP = q(16*lane - 1) + P1 and nextLoP = q(16*lane + 16) + P1 (q = L' - m), or a large sentinel at the
-// ends of the disparity range.  Returns the lane-local minimum of the new L.
-__device__ __forceinline__ uint32_t dp_step(uint32_t (&dp)[8], const uint32_t (&cost)[8], uint32_t M, uint32_t prevHiP,
-                                            uint32_t nextLoP, uint32_t P1v, uint32_t P2v) {
-    uint32_t q[8], qp[8];
+// One DP step for a lane's 16 disparities. dp[8] holds L' (previous pixel) on entry, L on exit; m = min_k L'(k).
+// With q = L' - m:  L(d) = C(d) + min(q(d), q(d-1) + P1, q(d+1) + P1, P2).
+//   qp = dp + (P1 - m)                     one 32-bit add per register (halves stay independent: q + P1 < 2^16)
+//   qc = min(dp - m, P2)                   VIADDMNMX.U16x2
+//   neighbours across registers            PRMT; across lanes: the packed qp of the adjacent lane by shuffle
+//   L  = min3(lower, upper, qc) + C        VIMNMX3.U16x2 + add
+// Returns the lane-local minimum of the new L.
+constexpr uint32_t kSentinel2 = 0x7FFF7FFFu;  // "no neighbour" at the ends of the disparity range
+
+template <int LPP>
+__device__ __forceinline__ uint32_t dp_step(uint32_t (&dp)[8], const uint32_t (&cost)[8], uint32_t m, int lane, uint32_t P1v,
+                                            uint32_t P2v) {
+    const uint32_t M = m * 0x10001u;
+    const uint32_t K = P1v - M;                           // packed (P1 - m) as one 32-bit offset
+    const uint32_t negM = ((0x10000u - m) & 0xFFFFu) * 0x10001u;  // per-half -m (mod 2^16)
+    uint32_t qp[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        q[i] = dp[i] - M;  // halves are >= m: no borrow between them
-        qp[i] = q[i] + P1v;
-    }
+    for (int i = 0; i < 8; ++i) qp[i] = dp[i] + K;
+    uint32_t up = __shfl_up_sync(0xFFFFFFFFu, qp[7], 1);
+    uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, qp[0], 1);
+    if (lane == 0) up = kSentinel2;
+    if (lane == LPP - 1) dn = kSentinel2;
     uint32_t sp[9];  // sp[i] = (q[2i-1] + P1, q[2i] + P1): lower neighbours of reg i, upper neighbours of reg i-1
-    sp[0] = __byte_perm(prevHiP, qp[0], 0x5410);
+    sp[0] = __byte_perm(up, qp[0], 0x5432);
 #pragma unroll
     for (int i = 1; i < 8; ++i) sp[i] = __byte_perm(qp[i - 1], qp[i], 0x5432);
-    sp[8] = __byte_perm(qp[7], nextLoP, 0x5432);
+    sp[8] = __byte_perm(qp[7], dn, 0x5432);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const uint32_t qc = __vminu2(q[i], P2v);
+        const uint32_t qc = __viaddmin_u16x2(dp[i], negM, P2v);
         dp[i] = __vimin3_u16x2(sp[i], sp[i + 1], qc) + cost[i];
     }
     uint32_t mn = __vimin3_u16x2(dp[0], dp[1], dp[2]);
@@ -125,23 +138,11 @@ __device__ __forceinline__ uint32_t dp_step(uint32_t (&dp)[8], const uint32_t (&
     return min(mn & 0xFFFFu, mn >> 16);
 }
 
-constexpr uint32_t kSentinel = 0x7FFFu;  // "no neighbour": larger than any q + P1, no u16 overflow
-
 template <int LPP>
 __device__ __forceinline__ uint32_t group_min(uint32_t v) {
 #pragma unroll
     for (int o = 1; o < LPP; o <<= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
     return v;
-}
-
-// neighbours across lanes of a group: q(16*lane - 1) + P1 and q(16*lane + 16) + P1
-template <int LPP>
-__device__ __forceinline__ void lane_neighbours(const uint32_t (&dp)[8], uint32_t M, uint32_t P1, int lane, uint32_t& prevHiP,
-                                                uint32_t& nextLoP) {
-    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, dp[7], 1);
-    const uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, dp[0], 1);
-    prevHiP = lane == 0 ? kSentinel : (((up - M) >> 16) + P1);
-    nextLoP = lane == LPP - 1 ? kSentinel : (((dn - M) & 0xFFFFu) + P1);
 }
 
 __device__ __forceinline__ void store_dp(uint8_t* dst, const uint32_t (&dp)[8]) {
@@ -153,9 +154,10 @@ __device__ __forceinline__ void store_dp(uint8_t* dst, const uint32_t (&dp)[8]) 
     __stcs(reinterpret_cast<uint4*>(dst), o);  // streaming store: the volume is not re-read before the WTA pass
 }
 
-__device__ __forceinline__ void load16(uint32_t* dst, const uint32_t* src) {
+template <int N>
+__device__ __forceinline__ void load_words(uint32_t* dst, const uint32_t* src) {  // N consecutive words, 16-byte aligned
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < N / 4; ++k) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + k);
         dst[4 * k] = v.x;
         dst[4 * k + 1] = v.y;
@@ -165,10 +167,14 @@ __device__ __forceinline__ void load16(uint32_t* dst, const uint32_t* src) {
 }
 
 // ---- horizontal -----------------------------------------------------------------------------------
-template <int D, int DX>
+// U = pixels per register-window refill (census rows are consumed in 16-byte pieces): the window holds the
+// 16 + U right-census words a lane needs for U consecutive pixels.
+constexpr int kHorizThreads = 128;
+constexpr int kHorizU = 8;
+template <int D, int DX, int U>
 __device__ __forceinline__ void horizontal_body(const PathArgs& a, uint8_t* __restrict__ volBase) {
     constexpr int LPP = D / 16;
-    constexpr int GPB = 128 / LPP;
+    constexpr int GPB = kHorizThreads / LPP;
     const int lane = threadIdx.x % LPP;
     const int group = threadIdx.x / LPP;
     const int f = blockIdx.y;
@@ -180,58 +186,55 @@ __device__ __forceinline__ void horizontal_body(const PathArgs& a, uint8_t* __re
     const uint32_t* cr = a.cenR + (size_t)f * a.cenFrameStride + (size_t)y * a.cenStride + a.cenMargin - 16 * lane - 16;
     uint8_t* vrow = volBase + (size_t)f * a.volFrameStride + (size_t)y * W * D + 16 * lane;
     const uint32_t P1v = pack16(a.P1, a.P1), P2v = pack16(a.P2, a.P2);
-    const int nChunks = (W + 15) >> 4;
+    const int nChunks = (W + U - 1) / U;
 
     uint32_t dp[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dp[i] = 0;
     uint32_t m = 0;
-    // S[k] = shifted right census word (x0 - 16*lane - 16 + k) of the current 16-pixel chunk starting at x0
-    uint32_t S[32];
+    // S[k] = shifted right census word (x0 - 16*lane - 16 + k) of the current U-pixel chunk starting at x0
+    uint32_t S[16 + U];
     {
-        const int x0 = DX > 0 ? 0 : 16 * (nChunks - 1);
-        load16(DX > 0 ? S : S + 16, cr + x0 + (DX > 0 ? 0 : 16));
+        const int x0 = DX > 0 ? 0 : U * (nChunks - 1);
+        load_words<16>(DX > 0 ? S : S + U, cr + x0 + (DX > 0 ? 0 : U));
     }
     for (int c = 0; c < nChunks; ++c) {
-        const int x0 = DX > 0 ? 16 * c : 16 * (nChunks - 1 - c);
-        uint32_t Lw[16];
-        load16(Lw, cl + x0);
-        load16(DX > 0 ? S + 16 : S, cr + x0 + (DX > 0 ? 16 : 0));
+        const int x0 = DX > 0 ? U * c : U * (nChunks - 1 - c);
+        uint32_t Lw[U];
+        load_words<U>(Lw, cl + x0);
+        load_words<U>(DX > 0 ? S + 16 : S, cr + x0 + (DX > 0 ? 16 : 0));
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const int sidx = DX > 0 ? t : 15 - t;
+        for (int t = 0; t < U; ++t) {
+            const int sidx = DX > 0 ? t : U - 1 - t;
             const int x = x0 + sidx;
             if (x < W) {  // warp-uniform: every group of the warp is at the same column
                 uint32_t cost[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     cost[i] = pack16(__popc(Lw[sidx] ^ S[16 + sidx - 2 * i]), __popc(Lw[sidx] ^ S[16 + sidx - 2 * i - 1]));
-                const uint32_t M = pack16(m, m);
-                uint32_t prevHiP, nextLoP;
-                lane_neighbours<LPP>(dp, M, a.P1, lane, prevHiP, nextLoP);
-                m = group_min<LPP>(dp_step(dp, cost, M, prevHiP, nextLoP, P1v, P2v));
+                m = group_min<LPP>(dp_step<LPP>(dp, cost, m, lane, P1v, P2v));
                 if (valid) store_dp(vrow + (size_t)x * D, dp);
             }
         }
+        if (DX > 0) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            if (DX > 0)
-                S[k] = S[k + 16];
-            else
-                S[k + 16] = S[k];
+            for (int k = 0; k < 16; ++k) S[k] = S[k + U];
+        } else {
+#pragma unroll
+            for (int k = 15; k >= 0; --k) S[k + U] = S[k];
         }
     }
 }
 
-template <int D>
-__global__ void __launch_bounds__(128) aggregate_horizontal_kernel(PathArgs a, int dirFirst, int both) {
+template <int D, int U>
+__global__ void __launch_bounds__(kHorizThreads) aggregate_horizontal_kernel(PathArgs a, int dirFirst, int both) {
     // blockIdx.z selects the direction when both are fused in one launch
     const int dir = both ? (blockIdx.z == 0 ? 1 : -1) : dirFirst;
     uint8_t* vol = (both && blockIdx.z == 1) ? a.vol2 : a.vol;
     if (dir > 0)
-        horizontal_body<D, 1>(a, vol);
+        horizontal_body<D, 1, U>(a, vol);
     else
-        horizontal_body<D, -1>(a, vol);
+        horizontal_body<D, -1, U>(a, vol);
 }
 
 // ---- vertical -------------------------------------------------------------------------------------
@@ -286,10 +289,7 @@ __global__ void __launch_bounds__(128) aggregate_vertical_kernel(PathArgs a, int
 #pragma unroll
             for (int i = 0; i < 8; ++i)
                 cost[i] = pack16(__popc(Lw[c] ^ S[16 + c - 2 * i]), __popc(Lw[c] ^ S[16 + c - 2 * i - 1]));
-            const uint32_t M = pack16(m[c], m[c]);
-            uint32_t prevHiP, nextLoP;
-            lane_neighbours<LPP>(dp[c], M, a.P1, lane, prevHiP, nextLoP);
-            m[c] = group_min<LPP>(dp_step(dp[c], cost, M, prevHiP, nextLoP, P1v, P2v));
+            m[c] = group_min<LPP>(dp_step<LPP>(dp[c], cost, m[c], lane, P1v, P2v));
             if (valid && x0 + c < W) store_dp(vbase + ((size_t)y * W + c) * D, dp[c]);
         }
     }
@@ -362,10 +362,7 @@ __global__ void __launch_bounds__(128) aggregate_path_kernel(PathArgs a) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) cost[i] = 0;
         }
-        const uint32_t M = pack16(m, m);
-        uint32_t prevHiP, nextLoP;
-        lane_neighbours<LPP>(dp, M, a.P1, lane, prevHiP, nextLoP);
-        const uint32_t lm = group_min<LPP>(dp_step(dp, cost, M, prevHiP, nextLoP, P1v, P2v));
+        const uint32_t lm = group_min<LPP>(dp_step<LPP>(dp, cost, m, lane, P1v, P2v));
         if (act) {
             m = lm;
             store_dp(vol + ((size_t)y * W + x) * D + 16 * lane, dp);
@@ -388,8 +385,8 @@ static void launch_paths_D(cartb200_ctx* c, PathArgs a, int n, int p0, int p1, c
         const bool pair = (p == 0 || p == 2) && p + 1 < p1;
         a.vol2 = pair ? c->volumes + (size_t)(p + 1) * c->volPathStride : nullptr;
         if (a.dy == 0) {
-            dim3 grid(ceilDiv(a.H, GPB), n, pair ? 2 : 1);
-            aggregate_horizontal_kernel<D><<<grid, 128, 0, s>>>(a, a.dx, pair ? 1 : 0);
+            dim3 grid(ceilDiv(a.H, kHorizThreads / (D / 16)), n, pair ? 2 : 1);
+            aggregate_horizontal_kernel<D, kHorizU><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0);
         } else if (a.dx == 0) {
             dim3 grid(ceilDiv(ceilDiv(a.W, 4), GPB), n, pair ? 2 : 1);
             aggregate_vertical_kernel<D><<<grid, 128, 0, s>>>(a, a.dy, pair ? 1 : 0);
@@ -435,133 +432,187 @@ int launch_aggregate_range(cartb200_ctx* c, int n, int p0, int p1, cudaStream_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Winner-takes-all (D5 + D6).  One CTA per image row; the row is processed in chunks of CH pixels.
-// LPP lanes per pixel, 16 disparities per lane: the P path volumes are read once with 16-byte loads,
-// summed to u16, kept in a shared-memory ring of (CH + D) pixels for the right-image minimum
-// dR(x) = argmin_d S(x+d, d), which lags the left pass by D-1 pixels.
+// Winner-takes-all (D5 + D6).  A group of LPP = D/16 lanes walks along a segment of one image row; each
+// lane owns 16 disparities.  Per pixel the P path volumes are read once (one 16-byte load per lane and
+// path: a group reads whole 128-byte lines), summed to u16x2, and turned into 32-bit keys (S << 16 | d):
+//   * left image:  the two smallest keys by a min/max tournament in registers + log2(LPP) shuffle rounds,
+//     uniqueness test and integer sub-pixel refinement on the group's first lane (the two neighbours of the
+//     winner come from a per-group shared-memory stash of the summed vector);
+//   * right image: dR(r) = argmin_d S(r + d, d) is accumulated systolically - a running minimum per
+//     disparity slot that moves one slot up per pixel (register renaming by a 16-fold unroll, one shuffle per
+//     step between lanes), so a right pixel leaves the last slot exactly when all its candidates have been
+//     seen.  Results are merged into a u32 key image with atomicMin, which also joins the partial minima of
+//     adjacent segments.  No shared-memory ring, no modulo arithmetic, no block barrier.
 struct WtaArgs {
     const uint8_t* vol;
     size_t volPathStride, volFrameStride;
-    int P, W, H;
+    int W, H;
     uint16_t* left;
-    uint16_t* right;
     size_t pitch;  // elements
+    uint32_t* rightKey;
+    size_t rkPitch;  // elements
     float uniq;
+    int nSeg, segLen, nItems;
 };
 
-template <int D, int CH>
-__global__ void __launch_bounds__(256) wta_kernel(WtaArgs a) {
+constexpr uint32_t kKeyInf = 0xFFFFFFFFu;
+
+// two smallest of 16 distinct keys: 8 compare-exchanges + 7 merges of sorted pairs
+__device__ __forceinline__ void top2_of16(const uint32_t (&k)[16], uint32_t& b1, uint32_t& b2) {
+    uint32_t lo[8], hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        lo[i] = min(k[2 * i], k[2 * i + 1]);
+        hi[i] = max(k[2 * i], k[2 * i + 1]);
+    }
+#pragma unroll
+    for (int n = 4; n >= 1; n >>= 1)
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const uint32_t m1 = min(lo[i], lo[i + n]);
+            const uint32_t m2 = min(max(lo[i], lo[i + n]), min(hi[i], hi[i + n]));
+            lo[i] = m1;
+            hi[i] = m2;
+        }
+    b1 = lo[0];
+    b2 = hi[0];
+}
+
+template <int D, int P>
+__global__ void __launch_bounds__(128) wta_walk_kernel(WtaArgs a) {
     constexpr int LPP = D / 16;
-    constexpr int PPI = 256 / LPP;  // pixels per CTA iteration
-    constexpr int R = CH + D;       // ring size in pixels
-    extern __shared__ uint16_t ring[];  // [R][D]
-    const int y = blockIdx.x, f = blockIdx.y;
-    const int W = a.W;
+    constexpr int GPB = 128 / LPP;
+    __shared__ __align__(16) uint16_t stash[2][GPB][D];
     const int lane = threadIdx.x % LPP, grp = threadIdx.x / LPP;
-    const uint8_t* vbase = a.vol + (size_t)f * a.volFrameStride + (size_t)y * W * D + 16 * lane;
+    const int item = blockIdx.x * GPB + grp;
+    const bool live = item < a.nItems;
+    int seg = 0, y = 0, f = 0;
+    if (live) {
+        seg = item % a.nSeg;
+        const int row = item / a.nSeg;
+        y = row % a.H;
+        f = row / a.H;
+    }
+    const int W = a.W;
+    const int x0 = seg * a.segLen;
+    const int x1 = live ? min(W, x0 + a.segLen) : x0;
+    const int T = (a.segLen + 15) & ~15;  // same trip count for every group of the warp (shuffles inside)
+    const uint8_t* vb = a.vol + (size_t)f * a.volFrameStride + ((size_t)y * W + x0) * D + 16 * lane;
     uint16_t* outL = a.left + ((size_t)f * a.H + y) * a.pitch;
-    uint16_t* outR = a.right + ((size_t)f * a.H + y) * a.pitch;
-    const unsigned gmask = 0xFFFFFFFFu;
-    const int nChunks = (W + CH - 1) / CH;
-    int rightNext = 0;  // next right pixel to finalise
-    for (int ck = 0; ck <= nChunks; ++ck) {
-        // ---- left pass over chunk ck -------------------------------------------------------
-        if (ck < nChunks) {
-            for (int px = grp; px < CH; px += PPI) {
-                const int x = ck * CH + px;
-                const bool in = x < W;
-                uint32_t S[8];
+    uint32_t* rk = a.rightKey + ((size_t)f * a.H + y) * a.rkPitch;
+    const uint32_t dbase = 16u * lane;
+
+    uint32_t RM[16];  // running minima; logical slot j (disparity dbase + j) at step t lives in RM[(j - t) & 15]
 #pragma unroll
-                for (int i = 0; i < 8; ++i) S[i] = 0;
-                if (in) {
-                    for (int p = 0; p < a.P; ++p) {
-                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(vbase + (size_t)p * a.volPathStride + (size_t)x * D));
-                        S[0] += __byte_perm(v.x, 0, 0x4140);
-                        S[1] += __byte_perm(v.x, 0, 0x4342);
-                        S[2] += __byte_perm(v.y, 0, 0x4140);
-                        S[3] += __byte_perm(v.y, 0, 0x4342);
-                        S[4] += __byte_perm(v.z, 0, 0x4140);
-                        S[5] += __byte_perm(v.z, 0, 0x4342);
-                        S[6] += __byte_perm(v.w, 0, 0x4140);
-                        S[7] += __byte_perm(v.w, 0, 0x4342);
-                    }
-                    uint4* dst = reinterpret_cast<uint4*>(ring + (size_t)(x % R) * D + 16 * lane);
-                    dst[0] = make_uint4(S[0], S[1], S[2], S[3]);
-                    dst[1] = make_uint4(S[4], S[5], S[6], S[7]);
-                }
-                // top-2 over packed (S << 16 | d)
-                uint32_t b1 = 0xFFFFFFFFu, b2 = 0xFFFFFFFFu;
+    for (int j = 0; j < 16; ++j) RM[j] = kKeyInf;
+    uint4 v[P];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint32_t d0 = 16 * lane + 2 * i;
-                    const uint32_t p0 = (S[i] << 16) | d0, p1 = (S[i] & 0xFFFF0000u) | (d0 + 1);
-                    b2 = min(b2, max(b1, p0));
-                    b1 = min(b1, p0);
-                    b2 = min(b2, max(b1, p1));
-                    b1 = min(b1, p1);
-                }
+    for (int p = 0; p < P; ++p)
+        v[p] = x0 < x1 ? __ldg(reinterpret_cast<const uint4*>(vb + (size_t)p * a.volPathStride)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+
+    for (int t0 = 0; t0 < T; t0 += 16) {
 #pragma unroll
-                for (int o = 1; o < LPP; o <<= 1) {
-                    const uint32_t o1 = __shfl_xor_sync(gmask, b1, o), o2 = __shfl_xor_sync(gmask, b2, o);
-                    b2 = min(min(b2, o2), max(b1, o1));
-                    b1 = min(b1, o1);
-                }
-                __syncwarp();
-                if (in && lane == 0) {
-                    const int c1 = (int)(b1 >> 16), d1 = (int)(b1 & 0xFFFF), c2 = (int)(b2 >> 16), d2 = (int)(b2 & 0xFFFF);
-                    const bool reject = (__fmul_rn((float)c2, a.uniq) < (float)c1) && (abs(d1 - d2) > 1);
-                    uint16_t v = 0xFFFF;
-                    if (!reject) {
-                        int subp = d1 << 4;
-                        if (d1 > 0 && d1 < D - 1) {
-                            const uint16_t* Sx = ring + (size_t)(x % R) * D;
-                            const int l = Sx[d1 - 1], r = Sx[d1 + 1];
-                            const int numer = l - r, denom = l - 2 * c1 + r;
-                            if (denom != 0) subp += ((numer << 4) + denom) / (2 * denom);
-                        }
-                        v = (uint16_t)subp;
-                    }
-                    outL[x] = v;
-                }
+        for (int t = 0; t < 16; ++t) {
+            const int x = x0 + t0 + t;
+            const bool act = x < x1;
+            // ---- sum of the P path costs, u16x2 (d, d+1) in natural order ----
+            uint32_t S[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) S[i] = 0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                S[0] += __byte_perm(v[p].x, 0, 0x4140);
+                S[1] += __byte_perm(v[p].x, 0, 0x4342);
+                S[2] += __byte_perm(v[p].y, 0, 0x4140);
+                S[3] += __byte_perm(v[p].y, 0, 0x4342);
+                S[4] += __byte_perm(v[p].z, 0, 0x4140);
+                S[5] += __byte_perm(v[p].z, 0, 0x4342);
+                S[6] += __byte_perm(v[p].w, 0, 0x4140);
+                S[7] += __byte_perm(v[p].w, 0, 0x4342);
             }
-        }
-        __syncthreads();
-        // ---- right pass: pixels whose window [x', x'+D) is complete (or truncated by the row end) ----
-        const int avail = min(W, (ck + 1) * CH);  // left pixels < avail are in the ring
-        const int rightEnd = (ck >= nChunks - 1) ? W : max(0, avail - D + 1);
-        for (int xb = rightNext; xb < rightEnd; xb += PPI) {  // warp-uniform trip count (shuffles inside)
-            const int xr = xb + grp;
-            uint32_t best = 0xFFFFFFFFu;
-            if (xr < rightEnd) {
+            // prefetch the next pixel; past the segment end the vector becomes all-ones: its sums (255 P) lose
+            // against every real candidate, so inactive steps only keep the systolic array moving
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int d = 16 * lane + j;
-                    if (xr + d < W) {
-                        const uint32_t sv = ring[(size_t)((xr + d) % R) * D + d];
-                        best = min(best, (sv << 16) | (uint32_t)d);
-                    }
-                }
+            for (int p = 0; p < P; ++p)
+                v[p] = (x + 1 < x1) ? __ldg(reinterpret_cast<const uint4*>(vb + (size_t)p * a.volPathStride + (size_t)(t0 + t + 1) * D))
+                                    : make_uint4(~0u, ~0u, ~0u, ~0u);
+            uint4* st = reinterpret_cast<uint4*>(&stash[t & 1][grp][16 * lane]);
+            st[0] = make_uint4(S[0], S[1], S[2], S[3]);
+            st[1] = make_uint4(S[4], S[5], S[6], S[7]);
+            uint32_t key[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                key[2 * i] = S[i] * 65536u + (dbase + 2 * i);
+                key[2 * i + 1] = (S[i] & 0xFFFF0000u) | (dbase + 2 * i + 1);
             }
+            // ---- left: two smallest keys of the pixel ----
+            uint32_t b1, b2;
+            top2_of16(key, b1, b2);
 #pragma unroll
-            for (int o = 1; o < LPP; o <<= 1) best = min(best, __shfl_xor_sync(gmask, best, o));
-            if (lane == 0 && xr < rightEnd) outR[xr] = (uint16_t)(best & 0xFFFF);
+            for (int o = 1; o < LPP; o <<= 1) {
+                const uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, b1, o), o2 = __shfl_xor_sync(0xFFFFFFFFu, b2, o);
+                const uint32_t m2 = min(max(b1, o1), min(b2, o2));
+                b1 = min(b1, o1);
+                b2 = m2;
+            }
+            __syncwarp();  // stash visible to the group's first lane
+            if (act && lane == 0) {
+                const int c1 = (int)(b1 >> 16), d1 = (int)(b1 & 0xFFFF), c2 = (int)(b2 >> 16), d2 = (int)(b2 & 0xFFFF);
+                const bool reject = (__fmul_rn((float)c2, a.uniq) < (float)c1) && (abs(d1 - d2) > 1);
+                uint16_t r = 0xFFFF;
+                if (!reject) {
+                    int subp = d1 << 4;
+                    if (d1 > 0 && d1 < D - 1) {
+                        const uint16_t* Sx = stash[t & 1][grp];
+                        const int l = Sx[d1 - 1], rr = Sx[d1 + 1];
+                        const int numer = l - rr, denom = l - 2 * c1 + rr;
+                        if (denom != 0) subp += ((numer << 4) + denom) / (2 * denom);
+                    }
+                    r = (uint16_t)subp;
+                }
+                outL[x] = r;
+            }
+            // ---- right: systolic running minima ----
+            const int ph = (16 - t) & 15;  // physical register of logical slot 0 at this step (static after unrolling)
+            const uint32_t out = RM[ph];        // slot 15 of the previous step: its right pixel moves to the next lane
+            uint32_t in = __shfl_up_sync(0xFFFFFFFFu, out, 1, LPP);
+            if (lane == 0) in = kKeyInf;
+            if (lane == LPP - 1 && out != kKeyInf) {
+                const int r = x - 1 - (D - 1);  // complete: every candidate x' in [r, r + D) has been seen
+                if (r >= 0) atomicMin(rk + r, out);
+            }
+            RM[ph] = min(in, key[0]);
+#pragma unroll
+            for (int j = 1; j < 16; ++j) RM[(j + 16 - t) & 15] = min(RM[(j + 16 - t) & 15], key[j]);
         }
-        rightNext = max(rightNext, rightEnd);
-        __syncthreads();
-        if (ck >= nChunks - 1) break;
+    }
+    // flush: the last step had t = 15, so slot j sits in RM[(j + 1) & 15] and belongs to right pixel (x0 + T - 1) - d
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int r = x0 + T - 1 - (int)(dbase + j);
+        const uint32_t val = RM[(j + 1) & 15];
+        if (r >= 0 && r < W && val != kKeyInf) atomicMin(rk + r, val);
     }
 }
 
-template <int D, int CH>
-static int launch_wta_D(cartb200_ctx* c, const WtaArgs& a, int n, cudaStream_t s) {
-    const size_t smem = (size_t)(CH + D) * D * sizeof(uint16_t);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(wta_kernel<D, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
-    dim3 grid(c->H, n);
-    wta_kernel<D, CH><<<grid, 256, smem, s>>>(a);
+template <int D>
+static int launch_wta_D(cartb200_ctx* c, WtaArgs& a, int n, cudaStream_t s) {
+    constexpr int GPB = 128 / (D / 16);
+    // segments per row: enough groups to fill the machine (~48 warps per SM), at most 8, at least D pixels long
+    const long rows = (long)n * c->H;
+    const long wantGroups = (long)kNumSMs * 48 * (32 / (D / 16));
+    int nSeg = (int)std::min<long>(8, std::max<long>(1, (wantGroups + rows - 1) / rows));
+    nSeg = std::max(1, std::min(nSeg, c->W / (2 * D)));
+    a.nSeg = nSeg;
+    a.segLen = (ceilDiv(c->W, nSeg) + 15) & ~15;
+    a.nSeg = ceilDiv(c->W, a.segLen);
+    a.nItems = (int)(rows * a.nSeg);
+    CB_CHECK_CUDA(c, cudaMemsetAsync(c->wtaR, 0xFF, (size_t)n * c->H * c->rkPitch * sizeof(uint32_t), s));
+    dim3 grid(ceilDiv(a.nItems, GPB));
+    if (c->P == 4)
+        wta_walk_kernel<D, 4><<<grid, 128, 0, s>>>(a);
+    else
+        wta_walk_kernel<D, 8><<<grid, 128, 0, s>>>(a);
     CB_LAUNCH_CHECK(c);
     return CARTB200_OK;
 }
@@ -571,17 +622,17 @@ int launch_wta(cartb200_ctx* c, int n, cudaStream_t s) {
     a.vol = c->volumes;
     a.volPathStride = c->volPathStride;
     a.volFrameStride = c->volFrameStride;
-    a.P = c->P;
     a.W = c->W;
     a.H = c->H;
     a.left = c->wtaL;
-    a.right = c->wtaR;
     a.pitch = c->dispPitch / 2;
+    a.rightKey = c->wtaR;
+    a.rkPitch = c->rkPitch;
     a.uniq = (float)(100 - c->cfg.uniqueness_ratio) / 100.0f;
     switch (c->D) {
-        case 64: return launch_wta_D<64, 64>(c, a, n, s);
-        case 128: return launch_wta_D<128, 64>(c, a, n, s);
-        case 256: return launch_wta_D<256, 32>(c, a, n, s);
+        case 64: return launch_wta_D<64>(c, a, n, s);
+        case 128: return launch_wta_D<128>(c, a, n, s);
+        case 256: return launch_wta_D<256>(c, a, n, s);
     }
     c->err = "num_disparities must be 64, 128 or 256";
     return CARTB200_E_UNSUPPORTED;
@@ -605,29 +656,44 @@ __host__ __device__ __forceinline__ uint32_t median9(uint32_t* v) {
     cswap(v[4], v[2]);
     return v[4];
 }
-__device__ __forceinline__ uint32_t median_at(const uint16_t* img, size_t pitch, int W, int H, int x, int y) {
-    if (x < 1 || y < 1 || x >= W - 1 || y >= H - 1) return __ldg(img + (size_t)y * pitch + x);
+template <typename T>  // T = uint16_t (left sub-pixel image) or uint32_t (right key image: disparity in the low half)
+__device__ __forceinline__ uint32_t median_at(const T* img, size_t pitch, int W, int H, int x, int y) {
+    if (x < 1 || y < 1 || x >= W - 1 || y >= H - 1) return __ldg(img + (size_t)y * pitch + x) & 0xFFFFu;
     uint32_t v[9];
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) v[j * 3 + i] = __ldg(img + (size_t)(y + j - 1) * pitch + x + i - 1);
+        for (int i = 0; i < 3; ++i) v[j * 3 + i] = __ldg(img + (size_t)(y + j - 1) * pitch + x + i - 1) & 0xFFFFu;
     return median9(v);
 }
 
-__global__ void __launch_bounds__(256) sgm_post_kernel(const uint16_t* __restrict__ wl, const uint16_t* __restrict__ wr,
-                                                       size_t pitch, const uint8_t* __restrict__ grayL, size_t grayPitch,
+__global__ void __launch_bounds__(256) sgm_post_kernel(const uint16_t* __restrict__ wl, const uint32_t* __restrict__ wr,
+                                                       size_t pitch, size_t rkPitch, const uint8_t* __restrict__ grayL, size_t grayPitch,
                                                        ImgBatch<int16_t> out, int W, int H, int minDisp) {
     const int f = blockIdx.z, y = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= W) return;
     const uint16_t* L = wl + (size_t)f * H * pitch;
-    const uint16_t* Rr = wr + (size_t)f * H * pitch;
+    const uint32_t* Rr = wr + (size_t)f * H * rkPitch;
     const uint32_t org = median_at(L, pitch, W, H, x, y);
     const int d = (int)org >> 4;
     const int k = x - d;
     bool invalid = grayL[((size_t)f * H + y) * grayPitch + x] == 0 || org == 0xFFFFu;
-    if (!invalid && k >= 0 && k < W) invalid = abs((int)median_at(Rr, pitch, W, H, k, y) - d) > 1;
+    if (!invalid && k >= 0 && k < W) invalid = abs((int)median_at(Rr, rkPitch, W, H, k, y) - d) > 1;
     out.frame(f).at(x, y) = invalid ? (int16_t)((minDisp - 1) * 16) : (int16_t)(uint16_t)(org + minDisp * 16);
+}
+
+__global__ void right_key_to_u16_kernel(const uint32_t* __restrict__ keys, size_t rkPitch, uint16_t* __restrict__ out,
+                                        size_t pitch, int W, int rows) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < W && y < rows) out[(size_t)y * pitch + x] = (uint16_t)(keys[(size_t)y * rkPitch + x] & 0xFFFFu);
+}
+
+// parity/debug access: integer right disparities as a u16 image (cartb200_sgm_intermediate selector 4)
+int launch_right_u16(cartb200_ctx* c, int n, uint16_t* out, cudaStream_t s) {
+    dim3 grid(ceilDiv(c->W, 256), n * c->H);
+    right_key_to_u16_kernel<<<grid, 256, 0, s>>>(c->wtaR, c->rkPitch, out, c->dispPitch / 2, c->W, n * c->H);
+    CB_LAUNCH_CHECK(c);
+    return CARTB200_OK;
 }
 
 uint32_t debug_median9_host(const uint16_t* v9) {
@@ -638,7 +704,7 @@ uint32_t debug_median9_host(const uint16_t* v9) {
 
 int launch_sgm_post(cartb200_ctx* c, int n, ImgBatch<int16_t> disp, cudaStream_t s) {
     dim3 grid(ceilDiv(c->W, 256), c->H, n);
-    sgm_post_kernel<<<grid, 256, 0, s>>>(c->wtaL, c->wtaR, c->dispPitch / 2, c->grayL, c->grayPitch, disp, c->W, c->H,
+    sgm_post_kernel<<<grid, 256, 0, s>>>(c->wtaL, c->wtaR, c->dispPitch / 2, c->rkPitch, c->grayL, c->grayPitch, disp, c->W, c->H,
                                          c->cfg.min_disparity);
     CB_LAUNCH_CHECK(c);
     return CARTB200_OK;

@@ -207,16 +207,18 @@ def test_sequence_naive_pipeline(gpu, provider):
         assert any(r["params"][2:] != [0, 0, 0, 0] for r in ref), "peak provider never fired on the test data"
 
 
+@pytest.mark.parametrize("max_batch", [2, 8])
 @pytest.mark.parametrize("provider", ["static", "histogram_peak"])
-def test_sequence_superpixel_pipeline(gpu, provider):
-    # reset every 8 frames so that 21 frames span chunks [1..7], [8..15], [16..21]; 2 slots force two groups
+def test_sequence_superpixel_pipeline(gpu, provider, max_batch):
+    # reset every 8 frames so that 21 frames span chunks [1..7], [8..15], [16..21]; 2 slots force two groups,
+    # 8 slots put all three chunks in one group whose SGM/derivative stages run two steps per launch
     W, H, D, n = 160, 64, 64, 21
     seq, frames = _frames(W, H, D, n, tint=True)
     cfgd = dict(D=D, radius=2, iters=1)
     ref = rp.sp_sequence(frames, cfgd, provider=provider, update=5, reset=2, initial=6, steady=3, sp_reset=8, block=8)
     L = np.stack([f[0] for f in frames])
     R = np.stack([f[1] for f in frames])
-    cfg = cb.Config(W, H, max_batch=2, num_disparities=D, smoothing_radius=2, smoothing_iterations=1, sp_block_size=8)
+    cfg = cb.Config(W, H, max_batch=max_batch, num_disparities=D, smoothing_radius=2, smoothing_iterations=1, sp_block_size=8)
     opts = cb.SequenceOptions(pipeline=1, provider=0 if provider == "static" else 1, update_interval=5, reset_interval=2,
                               sp_initial_iterations=6, sp_iterations=3, sp_reset_iterations=8)
     with cb.Context(cfg) as ctx:

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--height", type=int, default=375)
     ap.add_argument("--disp", type=int, default=128)
     ap.add_argument("--block", type=int, default=12)
+    ap.add_argument("--tag", default="")
     ap.add_argument("--once", action="store_true", help="run every stage exactly once (for ncu captures)")
     args = ap.parse_args()
     if args.once:
@@ -84,7 +85,7 @@ def main():
             extra = f"  {gbs:7.0f} GB/s  {gbs / peak:5.3f} (volume reads only)"
         print(f"  {k:26s} {v:9.3f} ms  ({v / B * 1e3:8.1f} us/frame){extra}")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "stage_bench.json"), "w"), indent=1)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"stage_bench{args.tag}.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -25,6 +25,16 @@ __global__ void k(uint32_t* out, uint32_t seed, int iters) {
                 if (OP == 7) a[i] = __shfl_xor_sync(0xffffffffu, a[i], 1);  // SHFL
                 if (OP == 8) a[i] = __vimin3_u16x2(a[i], a[(i + 1) & 7], c);  // VIMNMX3
                 if (OP == 9) a[i] = __popc(a[i] ^ c) + (a[(i+1)&7] & 0xff);   // LOP3 + POPC + LOP3 + IADD mix
+                if (OP == 10) a[i] = __reduce_min_sync(0xffffffffu, a[i]) + c;  // REDUX full warp
+                if (OP == 11) a[i] = __reduce_min_sync(0xffu << (threadIdx.x & 24), a[i]) + c;  // REDUX, 8-lane groups
+                if (OP == 12) {  // 8-lane group min by 3 shuffles
+                    uint32_t v = a[i];
+                    v = min(v, __shfl_xor_sync(0xffffffffu, v, 1));
+                    v = min(v, __shfl_xor_sync(0xffffffffu, v, 2));
+                    v = min(v, __shfl_xor_sync(0xffffffffu, v, 4));
+                    a[i] = v + c;
+                }
+                if (OP == 13) a[i] = __dp4a(a[i], 0x01010101u, a[(i + 1) & 7]);  // IDP4A
             }
         }
     }
@@ -32,6 +42,16 @@ __global__ void k(uint32_t* out, uint32_t seed, int iters) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += a[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void check_redux(uint32_t* out) {
+    const uint32_t v = (threadIdx.x * 2654435761u) >> 7;
+    out[threadIdx.x] = __reduce_min_sync(0xffu << (threadIdx.x & 24), v);
+    uint32_t w = v;
+    w = min(w, __shfl_xor_sync(0xffffffffu, w, 1));
+    w = min(w, __shfl_xor_sync(0xffffffffu, w, 2));
+    w = min(w, __shfl_xor_sync(0xffffffffu, w, 4));
+    out[32 + threadIdx.x] = w;
 }
 
 template <int OP>
@@ -69,5 +89,20 @@ int main() {
     run<7>("SHFL", 1);
     run<8>("VIMNMX3.U16x2", 1);
     run<9>("LOP3+POPC+LOP3+IADD", 4);
+    run<10>("REDUX.MIN full warp (+IADD)", 2);
+    run<11>("REDUX.MIN 8-lane masks (+IADD)", 2);
+    run<12>("3xSHFL+3xMIN group min (+IADD)", 7);
+    run<13>("IDP4A", 1);
+    // correctness of the group-masked REDUX against the shuffle tree
+    {
+        uint32_t* d;
+        cudaMalloc(&d, 64 * 4);
+        check_redux<<<1, 32>>>(d);
+        uint32_t h[64];
+        cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+        int bad = 0;
+        for (int i = 0; i < 32; ++i) bad += h[i] != h[32 + i];
+        printf("REDUX 8-lane-mask vs shuffle tree: %s\n", bad ? "MISMATCH" : "identical");
+    }
     return 0;
 }
