@@ -214,7 +214,8 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
             c->err = "cudaMemset failed";
             return fail(CARTB200_E_CUDA);
         }
-        if ((rc = devAlloc(c, &c->volumes, c->volPathStride * c->P))) return fail(rc);
+        // + 64 KiB: the WTA kernel reads (never uses) up to a few pixels past the end of a row segment
+        if ((rc = devAlloc(c, &c->volumes, c->volPathStride * c->P + (64 << 10)))) return fail(rc);
         if ((rc = devAlloc(c, &c->wtaL, B * H * c->dispPitch))) return fail(rc);
         c->rkPitch = alignUp(W, 32);
         if ((rc = devAlloc(c, &c->wtaR, B * H * c->rkPitch * sizeof(uint32_t)))) return fail(rc);

@@ -109,8 +109,8 @@ __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return hi
 constexpr uint32_t kSentinel2 = 0x7FFF7FFFu;  // "no neighbour" at the ends of the disparity range
 
 template <int LPP>
-__device__ __forceinline__ uint32_t dp_step(uint32_t (&dp)[8], const uint32_t (&cost)[8], uint32_t m, int lane, uint32_t P1v,
-                                            uint32_t P2v) {
+__device__ __forceinline__ uint32_t dp_step(uint32_t (&dp)[8], const uint32_t (&cost)[16], uint32_t m, int lane, uint32_t P1v,
+                                            uint32_t P2v) {  // cost[2i], cost[2i+1]: matching costs of disparities 2i, 2i+1
     const uint32_t M = m * 0x10001u;
     const uint32_t K = P1v - M;                           // packed (P1 - m) as one 32-bit offset
     const uint32_t negM = ((0x10000u - m) & 0xFFFFu) * 0x10001u;  // per-half -m (mod 2^16)
@@ -129,7 +129,7 @@ __device__ __forceinline__ uint32_t dp_step(uint32_t (&dp)[8], const uint32_t (&
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const uint32_t qc = __viaddmin_u16x2(dp[i], negM, P2v);
-        dp[i] = __vimin3_u16x2(sp[i], sp[i + 1], qc) + cost[i];
+        dp[i] = __vimin3_u16x2(sp[i], sp[i + 1], qc) + cost[2 * i] + (cost[2 * i + 1] << 16);
     }
     uint32_t mn = __vimin3_u16x2(dp[0], dp[1], dp[2]);
     mn = __vimin3_u16x2(mn, dp[3], dp[4]);
@@ -208,10 +208,9 @@ __device__ __forceinline__ void horizontal_body(const PathArgs& a, uint8_t* __re
             const int sidx = DX > 0 ? t : U - 1 - t;
             const int x = x0 + sidx;
             if (x < W) {  // warp-uniform: every group of the warp is at the same column
-                uint32_t cost[8];
+                uint32_t cost[16];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    cost[i] = pack16(__popc(Lw[sidx] ^ S[16 + sidx - 2 * i]), __popc(Lw[sidx] ^ S[16 + sidx - 2 * i - 1]));
+                for (int k = 0; k < 16; ++k) cost[k] = __popc(Lw[sidx] ^ S[16 + sidx - k]);
                 m = group_min<LPP>(dp_step<LPP>(dp, cost, m, lane, P1v, P2v));
                 if (valid) store_dp(vrow + (size_t)x * D, dp);
             }
@@ -285,10 +284,9 @@ __global__ void __launch_bounds__(128) aggregate_vertical_kernel(PathArgs a, int
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            uint32_t cost[8];
+            uint32_t cost[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                cost[i] = pack16(__popc(Lw[c] ^ S[16 + c - 2 * i]), __popc(Lw[c] ^ S[16 + c - 2 * i - 1]));
+            for (int k = 0; k < 16; ++k) cost[k] = __popc(Lw[c] ^ S[16 + c - k]);
             m[c] = group_min<LPP>(dp_step<LPP>(dp[c], cost, m[c], lane, P1v, P2v));
             if (valid && x0 + c < W) store_dp(vbase + ((size_t)y * W + c) * D, dp[c]);
         }
@@ -352,15 +350,15 @@ __global__ void __launch_bounds__(128) aggregate_path_kernel(PathArgs a) {
     uint32_t m = 0;
     for (int step = 0; step < maxLen; ++step) {
         const bool act = step < len;
-        uint32_t cost[8];
+        uint32_t cost[16];
         if (act) {
             const uint32_t l = __ldg(cl + (size_t)y * a.cenStride + x);
             const uint32_t* crow = cr + (size_t)y * a.cenStride + x;  // margins make every index valid
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cost[i] = pack16(__popc(l ^ __ldg(crow - 2 * i)), __popc(l ^ __ldg(crow - 2 * i - 1)));
+            for (int k = 0; k < 16; ++k) cost[k] = __popc(l ^ __ldg(crow - k));
         } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cost[i] = 0;
+            for (int k = 0; k < 16; ++k) cost[k] = 0;
         }
         const uint32_t lm = group_min<LPP>(dp_step<LPP>(dp, cost, m, lane, P1v, P2v));
         if (act) {
@@ -434,7 +432,7 @@ int launch_aggregate_range(cartb200_ctx* c, int n, int p0, int p1, cudaStream_t 
 // ---------------------------------------------------------------------------------------------
 // Winner-takes-all (D5 + D6).  A group of LPP = D/16 lanes walks along a segment of one image row; each
 // lane owns 16 disparities.  Per pixel the P path volumes are read once (one 16-byte load per lane and
-// path: a group reads whole 128-byte lines), summed to u16x2, and turned into 32-bit keys (S << 16 | d):
+// path: a group reads whole 128-byte lines), summed to u16x2, and turned into 32-bit keys (S << 8 | d):
 //   * left image:  the two smallest keys by a min/max tournament in registers + log2(LPP) shuffle rounds,
 //     uniqueness test and integer sub-pixel refinement on the group's first lane (the two neighbours of the
 //     winner come from a per-group shared-memory stash of the summed vector);
@@ -456,6 +454,7 @@ struct WtaArgs {
 };
 
 constexpr uint32_t kKeyInf = 0xFFFFFFFFu;
+constexpr uint32_t kKeyReal = 0x10000000u;  // real keys (S <= 255 * 8) are below; masked and empty ones above
 
 // two smallest of 16 distinct keys: 8 compare-exchanges + 7 merges of sorted pairs
 __device__ __forceinline__ void top2_of16(const uint32_t (&k)[16], uint32_t& b1, uint32_t& b2) {
@@ -496,25 +495,36 @@ __global__ void __launch_bounds__(128) wta_walk_kernel(WtaArgs a) {
     const int W = a.W;
     const int x0 = seg * a.segLen;
     const int x1 = live ? min(W, x0 + a.segLen) : x0;
-    const int T = (a.segLen + 15) & ~15;  // same trip count for every group of the warp (shuffles inside)
-    const uint8_t* vb = a.vol + (size_t)f * a.volFrameStride + ((size_t)y * W + x0) * D + 16 * lane;
+    const int T = a.segLen;  // multiple of 16; the same trip count for every group of the warp (shuffles inside)
+    // loads are unconditional (the volume allocation is padded): steps past the segment end read valid
+    // memory and are neutralised below
+    const uint8_t* vp = a.vol + (size_t)f * a.volFrameStride + ((size_t)y * W + x0) * D + 16 * lane;
     uint16_t* outL = a.left + ((size_t)f * a.H + y) * a.pitch;
     uint32_t* rk = a.rightKey + ((size_t)f * a.H + y) * a.rkPitch;
     const uint32_t dbase = 16u * lane;
+    // keys order by (S, d) with d < 256: one PRMT each - byte 0 = d from a constant register, bytes 1-2 = S,
+    // byte 3 = the high byte of S again (keeps the order; masked off when the cost is extracted)
+    uint32_t J[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) J[k] = (dbase + 4 * k) * 0x01010101u + 0x03020100u;
 
     uint32_t RM[16];  // running minima; logical slot j (disparity dbase + j) at step t lives in RM[(j - t) & 15]
 #pragma unroll
     for (int j = 0; j < 16; ++j) RM[j] = kKeyInf;
-    uint4 v[P];
+    uint4 va[P], vb[P];  // two pixels in flight
 #pragma unroll
-    for (int p = 0; p < P; ++p)
-        v[p] = x0 < x1 ? __ldg(reinterpret_cast<const uint4*>(vb + (size_t)p * a.volPathStride)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (int p = 0; p < P; ++p) {
+        va[p] = __ldg(reinterpret_cast<const uint4*>(vp + (size_t)p * a.volPathStride));
+        vb[p] = __ldg(reinterpret_cast<const uint4*>(vp + (size_t)p * a.volPathStride + D));
+    }
 
-    for (int t0 = 0; t0 < T; t0 += 16) {
+    for (int t0 = 0; t0 < T; t0 += 16, vp += 16 * D) {
+        const bool blockActive = __all_sync(0xFFFFFFFFu, x0 + t0 + 16 <= x1);
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
             const int x = x0 + t0 + t;
             const bool act = x < x1;
+            uint4(&v)[P] = (t & 1) ? vb : va;
             // ---- sum of the P path costs, u16x2 (d, d+1) in natural order ----
             uint32_t S[8];
 #pragma unroll
@@ -530,20 +540,23 @@ __global__ void __launch_bounds__(128) wta_walk_kernel(WtaArgs a) {
                 S[6] += __byte_perm(v[p].w, 0, 0x4140);
                 S[7] += __byte_perm(v[p].w, 0, 0x4342);
             }
-            // prefetch the next pixel; past the segment end the vector becomes all-ones: its sums (255 P) lose
-            // against every real candidate, so inactive steps only keep the systolic array moving
 #pragma unroll
-            for (int p = 0; p < P; ++p)
-                v[p] = (x + 1 < x1) ? __ldg(reinterpret_cast<const uint4*>(vb + (size_t)p * a.volPathStride + (size_t)(t0 + t + 1) * D))
-                                    : make_uint4(~0u, ~0u, ~0u, ~0u);
+            for (int p = 0; p < P; ++p)  // refill this buffer with the pixel two steps ahead
+                v[p] = __ldg(reinterpret_cast<const uint4*>(vp + (size_t)p * a.volPathStride + (t + 2) * D));
+            if (!blockActive) {  // warp-uniform: only the ragged tail of a segment takes this path
+                const uint32_t mask = act ? 0u : 0x7FFF7FFFu;  // inactive steps lose against every real candidate
+#pragma unroll
+                for (int i = 0; i < 8; ++i) S[i] |= mask;
+            }
             uint4* st = reinterpret_cast<uint4*>(&stash[t & 1][grp][16 * lane]);
             st[0] = make_uint4(S[0], S[1], S[2], S[3]);
             st[1] = make_uint4(S[4], S[5], S[6], S[7]);
             uint32_t key[16];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                key[2 * i] = S[i] * 65536u + (dbase + 2 * i);
-                key[2 * i + 1] = (S[i] & 0xFFFF0000u) | (dbase + 2 * i + 1);
+                // selector nibbles (byte 0..3): constant byte (4 + j % 4), cost low byte, cost high byte, cost high byte
+                key[2 * i] = __byte_perm(S[i], J[(2 * i) >> 2], 0x1104 + ((2 * i) & 3));
+                key[2 * i + 1] = __byte_perm(S[i], J[(2 * i + 1) >> 2], 0x3324 + ((2 * i + 1) & 3));
             }
             // ---- left: two smallest keys of the pixel ----
             uint32_t b1, b2;
@@ -555,29 +568,27 @@ __global__ void __launch_bounds__(128) wta_walk_kernel(WtaArgs a) {
                 b1 = min(b1, o1);
                 b2 = m2;
             }
-            __syncwarp();  // stash visible to the group's first lane
-            if (act && lane == 0) {
-                const int c1 = (int)(b1 >> 16), d1 = (int)(b1 & 0xFFFF), c2 = (int)(b2 >> 16), d2 = (int)(b2 & 0xFFFF);
+            __syncwarp();  // the stash of this step is complete
+            {   // every lane holds the same (b1, b2): branch-free finish, only the group's first lane stores
+                const int c1 = (int)((b1 >> 8) & 0xFFFF), d1 = (int)(b1 & 0xFF), c2 = (int)((b2 >> 8) & 0xFFFF), d2 = (int)(b2 & 0xFF);
                 const bool reject = (__fmul_rn((float)c2, a.uniq) < (float)c1) && (abs(d1 - d2) > 1);
-                uint16_t r = 0xFFFF;
-                if (!reject) {
-                    int subp = d1 << 4;
-                    if (d1 > 0 && d1 < D - 1) {
-                        const uint16_t* Sx = stash[t & 1][grp];
-                        const int l = Sx[d1 - 1], rr = Sx[d1 + 1];
-                        const int numer = l - rr, denom = l - 2 * c1 + rr;
-                        if (denom != 0) subp += ((numer << 4) + denom) / (2 * denom);
-                    }
-                    r = (uint16_t)subp;
-                }
-                outL[x] = r;
+                const uint16_t* Sx = stash[t & 1][grp];
+                const int l = Sx[max(d1 - 1, 0)], rr = Sx[min(d1 + 1, D - 1)];
+                const int numer = l - rr, denom = l - 2 * c1 + rr;
+                const bool interior = d1 > 0 && d1 < D - 1 && denom != 0;
+                // trunc(((numer << 4) + denom) / (2 denom)) in fp32: |numerator| <= 21744 and the quotient's distance
+                // to the next integer is >= 1 / |2 denom|, i.e. >= 4.6e-5 relative, so a reciprocal-multiply with
+                // a 1e-5 relative nudge away from zero truncates exactly
+                const float num = (float)((numer << 4) + denom), den = interior ? (float)(2 * denom) : 1.0f;
+                const int q = interior ? __float2int_rz(__fdividef(num, den) * 1.00001f) : 0;
+                if (act && lane == 0) outL[x] = reject ? (uint16_t)0xFFFF : (uint16_t)((d1 << 4) + q);
             }
             // ---- right: systolic running minima ----
             const int ph = (16 - t) & 15;  // physical register of logical slot 0 at this step (static after unrolling)
-            const uint32_t out = RM[ph];        // slot 15 of the previous step: its right pixel moves to the next lane
+            const uint32_t out = RM[ph];   // slot 15 of the previous step: its right pixel moves on to the next lane
             uint32_t in = __shfl_up_sync(0xFFFFFFFFu, out, 1, LPP);
             if (lane == 0) in = kKeyInf;
-            if (lane == LPP - 1 && out != kKeyInf) {
+            if (lane == LPP - 1 && out < kKeyReal) {
                 const int r = x - 1 - (D - 1);  // complete: every candidate x' in [r, r + D) has been seen
                 if (r >= 0) atomicMin(rk + r, out);
             }
@@ -591,7 +602,7 @@ __global__ void __launch_bounds__(128) wta_walk_kernel(WtaArgs a) {
     for (int j = 0; j < 16; ++j) {
         const int r = x0 + T - 1 - (int)(dbase + j);
         const uint32_t val = RM[(j + 1) & 15];
-        if (r >= 0 && r < W && val != kKeyInf) atomicMin(rk + r, val);
+        if (r >= 0 && r < W && val < kKeyReal) atomicMin(rk + r, val);
     }
 }
 
@@ -656,14 +667,15 @@ __host__ __device__ __forceinline__ uint32_t median9(uint32_t* v) {
     cswap(v[4], v[2]);
     return v[4];
 }
-template <typename T>  // T = uint16_t (left sub-pixel image) or uint32_t (right key image: disparity in the low half)
+template <typename T>  // T = uint16_t (left sub-pixel image) or uint32_t (right key image: disparity in the low byte)
 __device__ __forceinline__ uint32_t median_at(const T* img, size_t pitch, int W, int H, int x, int y) {
-    if (x < 1 || y < 1 || x >= W - 1 || y >= H - 1) return __ldg(img + (size_t)y * pitch + x) & 0xFFFFu;
+    constexpr uint32_t mask = sizeof(T) == 2 ? 0xFFFFu : 0xFFu;
+    if (x < 1 || y < 1 || x >= W - 1 || y >= H - 1) return __ldg(img + (size_t)y * pitch + x) & mask;
     uint32_t v[9];
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) v[j * 3 + i] = __ldg(img + (size_t)(y + j - 1) * pitch + x + i - 1) & 0xFFFFu;
+        for (int i = 0; i < 3; ++i) v[j * 3 + i] = __ldg(img + (size_t)(y + j - 1) * pitch + x + i - 1) & mask;
     return median9(v);
 }
 
@@ -685,7 +697,7 @@ __global__ void __launch_bounds__(256) sgm_post_kernel(const uint16_t* __restric
 __global__ void right_key_to_u16_kernel(const uint32_t* __restrict__ keys, size_t rkPitch, uint16_t* __restrict__ out,
                                         size_t pitch, int W, int rows) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x < W && y < rows) out[(size_t)y * pitch + x] = (uint16_t)(keys[(size_t)y * rkPitch + x] & 0xFFFFu);
+    if (x < W && y < rows) out[(size_t)y * pitch + x] = (uint16_t)(keys[(size_t)y * rkPitch + x] & 0xFFu);
 }
 
 // parity/debug access: integer right disparities as a u16 image (cartb200_sgm_intermediate selector 4)
