@@ -255,6 +255,18 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
         if ((rc = devAlloc(c, &c->spList, B * H * W * sizeof(uint32_t)))) return fail(rc);
         if ((rc = devAlloc(c, &c->spCount, B * sizeof(int)))) return fail(rc);
         if ((rc = devAlloc(c, &c->votes, B * (size_t)c->maxLabels * 4 * sizeof(uint32_t)))) return fail(rc);
+        {
+            std::vector<int> tileMap;
+            std::vector<uint32_t> tab;
+            build_sp_tile_tables(c->W, c->H, tileMap, tab);
+            if ((rc = devAlloc(c, &c->spTileMap, tileMap.size() * sizeof(int)))) return fail(rc);
+            if ((rc = devAlloc(c, &c->spTileTab, std::max<size_t>(tab.size(), 1) * sizeof(uint32_t)))) return fail(rc);
+            if (cudaMemcpy(c->spTileMap, tileMap.data(), tileMap.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+                (!tab.empty() && cudaMemcpy(c->spTileTab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess)) {
+                c->err = "cudaMemcpy failed";
+                return fail(CARTB200_E_CUDA);
+            }
+        }
         if ((rc = launch_sp_reset(c, c->B, nullptr, nullptr))) return fail(rc);
         if (cudaDeviceSynchronize() != cudaSuccess) {
             c->err = "superpixel initialisation failed";
@@ -284,6 +296,8 @@ void cartb200_destroy(cartb200_ctx* c) {
     cudaFree(c->spNew);
     cudaFree(c->spList);
     cudaFree(c->spCount);
+    cudaFree(c->spTileMap);
+    cudaFree(c->spTileTab);
     if (c->seq) {
         SeqScratch* q = static_cast<SeqScratch*>(c->seq);
         cudaFree(q->inL);

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/cartb200.h"
 
@@ -81,7 +82,9 @@ struct cartb200_ctx {
     double* spStats = nullptr;     // [B][maxLabels][kStatDoubles]
     uint16_t* spNew = nullptr;     // [B][H*W] decided label per list entry
     uint32_t* spList = nullptr;    // [B][H*W] listed border pixels (x | y << 16)
-    int* spCount = nullptr;        // [B] list lengths
+    int* spCount = nullptr;        // [B] move-list lengths
+    int* spTileMap = nullptr;      // [tilesY][tilesX] index into spTileTab, -1 = interior tile
+    uint32_t* spTileTab = nullptr; // [edge tiles][66*66] source pixel (y << 16 | x) of the reference's label tile
     // sequence runner scratch (lazy)
     void* seq = nullptr;
 };
@@ -122,4 +125,5 @@ int launch_sp_planeseg(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, Im
 int launch_sp_reset(cartb200_ctx* c, int n, const int* slotsDev, cudaStream_t s);
 int launch_sp_relax(cartb200_ctx* c, int n, const int* slotsDev, int iterations, ImgBatch<const uint8_t> left, ImgBatch<const int16_t> deriv, bool hasDeriv, ImgBatch<uint16_t> out, cudaStream_t s);
 int launch_border_map(cartb200_ctx* c, Img<const uint16_t> labels, Img<uint8_t> border, cudaStream_t s);
+void build_sp_tile_tables(int W, int H, std::vector<int>& tileMap, std::vector<uint32_t>& tab);
 }  // namespace cb
