@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cartb200", choices=["cartb200", "reference"])
     ap.add_argument("--frames", type=int, default=1000, help="frames per sequence (BASELINE.json configs[1]: 1000)")
-    ap.add_argument("--batch", type=int, default=16, help="frames (sequence chunks) per batched launch")
+    ap.add_argument("--batch", type=int, default=64, help="frames per batched launch (SGM stages); superpixel slots = sequence chunks")
     ap.add_argument("--pipeline", type=int, default=1, help="1 = superpixel pipeline (headline), 0 = naive")
     ap.add_argument("--cpu-sample", type=int, default=6)
     args = ap.parse_args()
