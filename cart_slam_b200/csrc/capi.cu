@@ -32,6 +32,9 @@ struct SeqScratch {
     int32_t* histHost = nullptr;  // pinned
     int32_t* paramsHost = nullptr;  // pinned [n][4]
     cudaStream_t copyStream = nullptr;
+    cudaStream_t spStream = nullptr;       // superpixel relaxation runs beside the SGM stages of the next batch
+    std::vector<cudaEvent_t> evBatch;      // batch k: disparity + derivative done (recorded on the main stream)
+    cudaEvent_t evStart = nullptr, evSpDone = nullptr;
     cudaEvent_t evIn[2] = {nullptr, nullptr};
     size_t inCap = 0, inRCap = 0, dispCap = 0, derivCap = 0, labelsCap = 0, planesCap = 0, histCap = 0, unsmCap = 0;
 };
@@ -311,6 +314,10 @@ void cartb200_destroy(cartb200_ctx* c) {
         cudaFreeHost(q->histHost);
         cudaFreeHost(q->paramsHost);
         if (q->copyStream) cudaStreamDestroy(q->copyStream);
+        if (q->spStream) cudaStreamDestroy(q->spStream);
+        for (auto& e : q->evBatch) cudaEventDestroy(e);
+        if (q->evStart) cudaEventDestroy(q->evStart);
+        if (q->evSpDone) cudaEventDestroy(q->evSpDone);
         for (auto& e : q->evIn)
             if (e) cudaEventDestroy(e);
         delete q;
@@ -657,6 +664,9 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
     if (!q->copyStream) {
         CB_CHECK_CUDA(c, cudaStreamCreateWithFlags(&q->copyStream, cudaStreamNonBlocking));
         for (auto& e : q->evIn) CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CB_CHECK_CUDA(c, cudaStreamCreateWithFlags(&q->spStream, cudaStreamNonBlocking));
+        CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&q->evStart, cudaEventDisableTiming));
+        CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&q->evSpDone, cudaEventDisableTiming));
     }
     const bool peak = o->provider == 1;
     const bool sp = o->pipeline == 1;
@@ -665,7 +675,9 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
         if ((rc = ensureCap(c, &q->inL, &q->inCap, bgrFrame * n))) return rc;
         if ((rc = ensureCap(c, &q->inR, &q->inRCap, bgrFrame * n))) return rc;
     }
-    const size_t nStore = (sp && peak) ? (size_t)n : B;  // frames whose derivative/labels must be kept
+    // superpixel pipeline: derivative and label images are kept per frame (the relaxation stream lags behind the
+    // SGM stream, and the histogram-peak provider needs them again in the second phase)
+    const size_t nStore = sp ? (size_t)n : B;
     if ((rc = ensureCap(c, &q->disp, &q->dispCap, pxFrame * 2 * (dispOut ? (size_t)n : B)))) return rc;
     if ((rc = ensureCap(c, &q->deriv, &q->derivCap, pxFrame * (sp ? 4 : 2) * nStore))) return rc;
     if (sp && (rc = ensureCap(c, &q->labels, &q->labelsCap, pxFrame * 2 * nStore))) return rc;
@@ -745,11 +757,6 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
 
     // ---------------- superpixel pipeline ------------------------------------------------------------
     // virtual ids: chunk k covers ids [k*R, k*R + R); frame index (0-based) = id - start_id.
-    if (inputsOnHost) {
-        // TODO(perf): stream the upload step-major; the whole sequence is uploaded up front for now
-        CB_CHECK_CUDA(c, cudaMemcpyAsync(q->inL, inL, bgrFrame * n, cudaMemcpyHostToDevice, s));
-        CB_CHECK_CUDA(c, cudaMemcpyAsync(q->inR, inR, bgrFrame * n, cudaMemcpyHostToDevice, s));
-    }
     const int firstId = o->start_id, lastId = o->start_id + n - 1;
     const int k0 = firstId / R, k1 = lastId / R;  // chunk range
     const int nChunks = k1 - k0 + 1;
@@ -757,11 +764,14 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
         for (size_t j = 0; j < B; ++j) std::memcpy(q->paramsHost + 4 * j, hs.params + 2, 4 * sizeof(int32_t));
         if ((rc = uploadParams(c, (int)B, q->paramsHost, s))) return rc;
     }
-    // a sequence that starts at id 1 starts from the constructor's block initialisation (superpixels.cu:56-58)
-    if (firstId == 1 && (rc = launch_sp_reset(c, 1, slotIota(c), s))) return rc;
     // Chunks are grouped so that every chunk of a group owns one superpixel slot.  The SGM/derivative stages
     // have no frame-to-frame state, so they run on up to B frames at once: `nb` chunks x `k` consecutive
     // steps (two-level ImgBatch); only the superpixel relaxation advances step by step.
+    struct Batch {
+        int ca, nb, st, k, idA;
+        size_t fiA;  // frame index of (first chunk, first step)
+    };
+    std::vector<Batch> batches;
     const int maxSlots = (int)B;
     for (int g0 = 0; g0 < nChunks; g0 += maxSlots) {
         const int gN = std::min<int>(maxSlots, nChunks - g0);
@@ -789,82 +799,118 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
                 range(st + k, ca2, cb2);
                 if (ca2 != ca || cb2 != cb) break;
             }
-            const int nb = cb - ca, total = nb * k;
             const int idA = (k0 + g0 + ca) * R + st;
-            const size_t fiA = (size_t)(idA - firstId);  // frame index of (first chunk, first step)
-            const size_t fStride = (size_t)R;            // frames between consecutive chunks
-            const int* slots = slotIota(c) + ca;
-            auto seqBatch = [&](auto* base, size_t frameBytes) {  // frames in sequence order, two-level
-                using T = std::remove_pointer_t<decltype(base)>;
-                return ImgBatch<T>{(T*)((char*)base + frameBytes * fiA), 0, frameBytes * fStride, nb, frameBytes};
-            };
-            ImgBatch<const uint8_t> bl = seqBatch(devL, bgrFrame), br = seqBatch(devR, bgrFrame);
-            bl.pitch = br.pitch = W * 3;
-            // disparity (all `total` frames)
-            ImgBatch<int16_t> dB = dispOut ? seqBatch(dispDev, pxFrame * 2) : ImgBatch<int16_t>{dispDev, 0, pxFrame * 2};
-            dB.pitch = W * 2;
-            if ((rc = disparity_batch(c, total, bl, br, dB, s))) return rc;
-            // derivative + per-frame histograms (staged batch-contiguously, scattered to their frame slots below)
-            ImgBatch<int16_t> vB = peak ? seqBatch(q->deriv, pxFrame * 4) : ImgBatch<int16_t>{q->deriv, 0, pxFrame * 4};
-            vB.pitch = W * 4;
-            const ImgBatch<const int16_t> dBc{dB.data, dB.pitch, dB.frameStride, dB.inner, dB.outerStride};
-            if ((rc = launch_derivative(c, total, dBc, vB, q->hist, s))) return rc;
-            if (peak) {
-                for (int kk = 0; kk < k; ++kk)
-                    for (int j = 0; j < nb; ++j)
-                        CB_CHECK_CUDA(c, cudaMemcpyAsync(q->histHost + 512 * (fiA + j * fStride + kk),
-                                                         q->hist + 512 * (size_t)(kk * nb + j), 512 * sizeof(int32_t),
-                                                         cudaMemcpyDeviceToHost, s));
-            }
-            ImgBatch<uint16_t> lB = peak ? seqBatch(q->labels, pxFrame * 2) : ImgBatch<uint16_t>{q->labels, 0, pxFrame * 2};
-            lB.pitch = W * 2;
-            ImgBatch<uint8_t> pB = seqBatch(planesDev, pxFrame);
-            pB.pitch = W;
-            // superpixels, one step at a time: reset + iteration schedule (superpixels.cu:93-113)
-            for (int kk = 0; kk < k; ++kk) {
-                auto step = [&](auto batch) {  // the nb frames of step st + kk as a simple strided batch
-                    using BT = decltype(batch);
-                    if (batch.inner > 0) return BT{(decltype(batch.data))((char*)batch.data + batch.outerStride * kk), batch.pitch, batch.frameStride};
-                    return BT{(decltype(batch.data))((char*)batch.data + batch.frameStride * (size_t)kk * nb), batch.pitch, batch.frameStride};
-                };
-                const bool resetStep = st + kk == 0;  // id % R == 0
-                if (resetStep && (rc = launch_sp_reset(c, nb, slots, s))) return rc;
-                const ImgBatch<const uint8_t> sl = step(bl);
-                const ImgBatch<int16_t> svm = step(vB);
-                const ImgBatch<const int16_t> sv{svm.data, svm.pitch, svm.frameStride};
-                const ImgBatch<uint16_t> so = step(lB);
-                // id == 1 also gets the initial iteration count (only chunk 0 at step 1 can be id 1)
-                if (!resetStep && idA + kk == 1) {
-                    if ((rc = launch_sp_relax(c, 1, slots, o->sp_initial_iterations, sl, sv, true, so, s))) return rc;
-                    if (nb > 1 && (rc = launch_sp_relax(c, nb - 1, slots + 1, o->sp_iterations, sl.from(1), sv.from(1), true,
-                                                        so.from(1), s)))
-                        return rc;
-                } else {
-                    const int its = resetStep ? o->sp_initial_iterations : o->sp_iterations;
-                    if ((rc = launch_sp_relax(c, nb, slots, its, sl, sv, true, so, s))) return rc;
-                }
-            }
-            if (!peak) {
-                // static ranges: vote + assign right away (the same ranges for every frame of the batch)
-                const ImgBatch<const int16_t> vBc{vB.data, vB.pitch, vB.frameStride, vB.inner, vB.outerStride};
-                const ImgBatch<const uint16_t> lBc{lB.data, lB.pitch, lB.frameStride, lB.inner, lB.outerStride};
-                if ((rc = launch_sp_planeseg(c, total, vBc, lBc, c->maxLabels, c->paramsDev,
-                                             ImgBatch<uint8_t>{q->unsm, W, pxFrame}, pB, s)))
-                    return rc;
-            }
+            batches.push_back(Batch{ca, cb - ca, st, k, idA, (size_t)(idA - firstId)});
             st += k;
         }
     }
+    const size_t fStride = (size_t)R;  // frames between consecutive chunks
+    // inputs in host memory: batch b + 1 is uploaded on the copy stream (step-major: k consecutive frames of
+    // every chunk) while batch b computes
+    auto upload = [&](size_t bi) -> int {
+        if (!inputsOnHost || bi >= batches.size()) return CARTB200_OK;
+        const Batch& bt = batches[bi];
+        for (int j = 0; j < bt.nb; ++j) {
+            const size_t off = bgrFrame * (bt.fiA + j * fStride);
+            CB_CHECK_CUDA(c, cudaMemcpyAsync(q->inL + off, inL + off, bgrFrame * bt.k, cudaMemcpyHostToDevice, q->copyStream));
+            CB_CHECK_CUDA(c, cudaMemcpyAsync(q->inR + off, inR + off, bgrFrame * bt.k, cudaMemcpyHostToDevice, q->copyStream));
+        }
+        CB_CHECK_CUDA(c, cudaEventRecord(q->evIn[bi & 1], q->copyStream));
+        return CARTB200_OK;
+    };
+    // Two streams: `s` runs gray/census/aggregation/WTA/derivative of batch b + 1 while `spS` relaxes the
+    // superpixels of batch b.
+    cudaStream_t spS = q->spStream;
+    CB_CHECK_CUDA(c, cudaEventRecord(q->evStart, s));
+    CB_CHECK_CUDA(c, cudaStreamWaitEvent(spS, q->evStart, 0));
+    if (inputsOnHost) CB_CHECK_CUDA(c, cudaStreamWaitEvent(q->copyStream, q->evStart, 0));
+    // a sequence that starts at id 1 starts from the constructor's block initialisation (superpixels.cu:56-58)
+    if (firstId == 1 && (rc = launch_sp_reset(c, 1, slotIota(c), spS))) return rc;
+    std::vector<size_t> histPos((size_t)n, 0);  // frame -> row of the batch-ordered histogram staging buffer
+    size_t histRows = 0;
+    if ((rc = upload(0))) return rc;
+    for (size_t bi = 0; bi < batches.size(); ++bi) {
+        const Batch& bt = batches[bi];
+        const int nb = bt.nb, k = bt.k, total = nb * k;
+        const size_t fiA = bt.fiA;
+        const int* slots = slotIota(c) + bt.ca;
+        if (inputsOnHost) CB_CHECK_CUDA(c, cudaStreamWaitEvent(s, q->evIn[bi & 1], 0));
+        if ((rc = upload(bi + 1))) return rc;
+        auto seqBatch = [&](auto* base, size_t frameBytes) {  // frames in sequence order, two-level
+            using T = std::remove_pointer_t<decltype(base)>;
+            return ImgBatch<T>{(T*)((char*)base + frameBytes * fiA), 0, frameBytes * fStride, nb, frameBytes};
+        };
+        ImgBatch<const uint8_t> bl = seqBatch(devL, bgrFrame), br = seqBatch(devR, bgrFrame);
+        bl.pitch = br.pitch = W * 3;
+        // disparity (all `total` frames)
+        ImgBatch<int16_t> dB = dispOut ? seqBatch(dispDev, pxFrame * 2) : ImgBatch<int16_t>{dispDev, 0, pxFrame * 2};
+        dB.pitch = W * 2;
+        if ((rc = disparity_batch(c, total, bl, br, dB, s))) return rc;
+        // derivative + per-frame histograms (batch-ordered staging rows, one download at the end)
+        ImgBatch<int16_t> vB = seqBatch(q->deriv, pxFrame * 4);
+        vB.pitch = W * 4;
+        const ImgBatch<const int16_t> dBc{dB.data, dB.pitch, dB.frameStride, dB.inner, dB.outerStride};
+        if ((rc = launch_derivative(c, total, dBc, vB, q->hist + 512 * histRows, s))) return rc;
+        for (int kk = 0; kk < k; ++kk)
+            for (int j = 0; j < nb; ++j) histPos[fiA + j * fStride + kk] = histRows + (size_t)(kk * nb + j);
+        histRows += (size_t)total;
+        ImgBatch<uint16_t> lB = seqBatch(q->labels, pxFrame * 2);
+        lB.pitch = W * 2;
+        if (q->evBatch.size() <= bi) {
+            cudaEvent_t e;
+            CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            q->evBatch.push_back(e);
+        }
+        CB_CHECK_CUDA(c, cudaEventRecord(q->evBatch[bi], s));
+        CB_CHECK_CUDA(c, cudaStreamWaitEvent(spS, q->evBatch[bi], 0));
+        ImgBatch<uint8_t> pB = seqBatch(planesDev, pxFrame);
+        pB.pitch = W;
+        // superpixels, one step at a time: reset + iteration schedule (superpixels.cu:93-113)
+        for (int kk = 0; kk < k; ++kk) {
+            auto step = [&](auto batch) {  // the nb frames of step st + kk as a simple strided batch
+                using BT = decltype(batch);
+                return BT{(decltype(batch.data))((char*)batch.data + batch.outerStride * kk), batch.pitch, batch.frameStride};
+            };
+            const bool resetStep = bt.st + kk == 0;  // id % R == 0
+            if (resetStep && (rc = launch_sp_reset(c, nb, slots, spS))) return rc;
+            const ImgBatch<const uint8_t> sl = step(bl);
+            const ImgBatch<int16_t> svm = step(vB);
+            const ImgBatch<const int16_t> sv{svm.data, svm.pitch, svm.frameStride};
+            const ImgBatch<uint16_t> so = step(lB);
+            // id == 1 also gets the initial iteration count (only chunk 0 at step 1 can be id 1)
+            if (!resetStep && bt.idA + kk == 1) {
+                if ((rc = launch_sp_relax(c, 1, slots, o->sp_initial_iterations, sl, sv, true, so, spS))) return rc;
+                if (nb > 1 && (rc = launch_sp_relax(c, nb - 1, slots + 1, o->sp_iterations, sl.from(1), sv.from(1), true,
+                                                    so.from(1), spS)))
+                    return rc;
+            } else {
+                const int its = resetStep ? o->sp_initial_iterations : o->sp_iterations;
+                if ((rc = launch_sp_relax(c, nb, slots, its, sl, sv, true, so, spS))) return rc;
+            }
+        }
+        if (!peak) {
+            // static ranges: vote + assign right away (the same ranges for every frame of the batch)
+            const ImgBatch<const int16_t> vBc{vB.data, vB.pitch, vB.frameStride, vB.inner, vB.outerStride};
+            const ImgBatch<const uint16_t> lBc{lB.data, lB.pitch, lB.frameStride, lB.inner, lB.outerStride};
+            if ((rc = launch_sp_planeseg(c, total, vBc, lBc, c->maxLabels, c->paramsDev,
+                                         ImgBatch<uint8_t>{q->unsm, W, pxFrame}, pB, spS)))
+                return rc;
+        }
+    }
+    if (peak) CB_CHECK_CUDA(c, cudaMemcpyAsync(q->histHost, q->hist, histRows * 512 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CB_CHECK_CUDA(c, cudaEventRecord(q->evSpDone, spS));
+    CB_CHECK_CUDA(c, cudaStreamWaitEvent(s, q->evSpDone, 0));
+    bool planesCopied = false;
     if (peak) {
         // second phase: parameters in id order, then vote + assign for every frame
         CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
         std::vector<int32_t> hv(256);
         for (int i = 0; i < n; ++i) {
-            const int32_t* h = q->histHost + 512 * (size_t)i;
+            const int32_t* h = q->histHost + 512 * histPos[(size_t)i];
             for (int b = 0; b < 256; ++b) hv[b] = h[2 * b];  // channel 0 = vertical (sp_planeseg.cu:358-359)
             spUpdate(hs, *o, firstId + i, hv.data(), q->paramsHost + 4 * (size_t)i);
         }
-        for (int b0 = 0; b0 < n; b0 += (int)B) {
+        for (int b0 = 0, bi = 0; b0 < n; b0 += (int)B, ++bi) {
             const int nb = std::min<int>((int)B, n - b0);
             if ((rc = uploadParams(c, nb, q->paramsHost + 4 * (size_t)b0, s))) return rc;
             if ((rc = launch_sp_planeseg(c, nb, ImgBatch<const int16_t>{q->deriv + pxFrame * 2 * b0, W * 4, pxFrame * 4},
@@ -872,10 +918,21 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
                                          c->paramsDev, ImgBatch<uint8_t>{q->unsm, W, pxFrame},
                                          ImgBatch<uint8_t>{planesDev + pxFrame * b0, W, pxFrame}, s)))
                 return rc;
+            if (outputsOnHost) {  // download this batch while the next one is voted
+                CB_CHECK_CUDA(c, cudaEventRecord(q->evIn[bi & 1], s));
+                CB_CHECK_CUDA(c, cudaStreamWaitEvent(q->copyStream, q->evIn[bi & 1], 0));
+                CB_CHECK_CUDA(c, cudaMemcpyAsync(planesOut + pxFrame * b0, planesDev + pxFrame * b0, pxFrame * nb,
+                                                 cudaMemcpyDeviceToHost, q->copyStream));
+            }
+        }
+        if (outputsOnHost) {
+            CB_CHECK_CUDA(c, cudaEventRecord(q->evStart, q->copyStream));
+            CB_CHECK_CUDA(c, cudaStreamWaitEvent(s, q->evStart, 0));
+            planesCopied = true;
         }
     }
     if (outputsOnHost) {
-        CB_CHECK_CUDA(c, cudaMemcpyAsync(planesOut, planesDev, pxFrame * n, cudaMemcpyDeviceToHost, s));
+        if (!planesCopied) CB_CHECK_CUDA(c, cudaMemcpyAsync(planesOut, planesDev, pxFrame * n, cudaMemcpyDeviceToHost, s));
         if (dispOut) CB_CHECK_CUDA(c, cudaMemcpyAsync(dispOut, dispDev, pxFrame * 2 * n, cudaMemcpyDeviceToHost, s));
     }
     if (outputsOnHost || inputsOnHost) CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
