@@ -10,6 +10,7 @@
 // register as u16x2 and the recurrence runs on the DPX/video integer instructions of sm_90+/sm_100
 // (VIADDMNMX.U16x2, VIMNMX.U16x2, VIMNMX3) - no tensor cores: nothing here is a dense contraction.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -171,7 +172,7 @@ __device__ __forceinline__ void load_words(uint32_t* dst, const uint32_t* src) {
 // 16 + U right-census words a lane needs for U consecutive pixels.
 constexpr int kHorizThreads = 128;
 constexpr int kHorizU = 8;
-template <int D, int DX, int U>
+template <int D, int DX, int U, bool PF>
 __device__ __forceinline__ void horizontal_body(const PathArgs& a, uint8_t* __restrict__ volBase) {
     constexpr int LPP = D / 16;
     constexpr int GPB = kHorizThreads / LPP;
@@ -194,15 +195,31 @@ __device__ __forceinline__ void horizontal_body(const PathArgs& a, uint8_t* __re
     uint32_t m = 0;
     // S[k] = shifted right census word (x0 - 16*lane - 16 + k) of the current U-pixel chunk starting at x0
     uint32_t S[16 + U];
+    uint32_t Lw[U], Ln[U], Sn[U];  // current chunk's left words; next chunk's left / right words (prefetched)
     {
         const int x0 = DX > 0 ? 0 : U * (nChunks - 1);
         load_words<16>(DX > 0 ? S : S + U, cr + x0 + (DX > 0 ? 0 : U));
+        if (PF) {
+            load_words<U>(Ln, cl + x0);
+            load_words<U>(Sn, cr + x0 + (DX > 0 ? 16 : 0));
+        }
     }
     for (int c = 0; c < nChunks; ++c) {
         const int x0 = DX > 0 ? U * c : U * (nChunks - 1 - c);
-        uint32_t Lw[U];
-        load_words<U>(Lw, cl + x0);
-        load_words<U>(DX > 0 ? S + 16 : S, cr + x0 + (DX > 0 ? 16 : 0));
+        if (PF) {
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                Lw[k] = Ln[k];
+                (DX > 0 ? S + 16 : S)[k] = Sn[k];
+            }
+            // prefetch the next chunk (the zero margins make one chunk past either end readable)
+            const int xn = DX > 0 ? x0 + U : x0 - U;
+            load_words<U>(Ln, cl + xn);
+            load_words<U>(Sn, cr + xn + (DX > 0 ? 16 : 0));
+        } else {
+            load_words<U>(Lw, cl + x0);
+            load_words<U>(DX > 0 ? S + 16 : S, cr + x0 + (DX > 0 ? 16 : 0));
+        }
 #pragma unroll
         for (int t = 0; t < U; ++t) {
             const int sidx = DX > 0 ? t : U - 1 - t;
@@ -225,15 +242,15 @@ __device__ __forceinline__ void horizontal_body(const PathArgs& a, uint8_t* __re
     }
 }
 
-template <int D, int U>
-__global__ void __launch_bounds__(kHorizThreads) aggregate_horizontal_kernel(PathArgs a, int dirFirst, int both) {
+template <int D, int U, bool PF, int MINB>
+__global__ void __launch_bounds__(kHorizThreads, MINB) aggregate_horizontal_kernel(PathArgs a, int dirFirst, int both) {
     // blockIdx.z selects the direction when both are fused in one launch
     const int dir = both ? (blockIdx.z == 0 ? 1 : -1) : dirFirst;
     uint8_t* vol = (both && blockIdx.z == 1) ? a.vol2 : a.vol;
     if (dir > 0)
-        horizontal_body<D, 1, U>(a, vol);
+        horizontal_body<D, 1, U, PF>(a, vol);
     else
-        horizontal_body<D, -1, U>(a, vol);
+        horizontal_body<D, -1, U, PF>(a, vol);
 }
 
 // ---- vertical -------------------------------------------------------------------------------------
@@ -270,6 +287,8 @@ __global__ void __launch_bounds__(128) aggregate_vertical_kernel(PathArgs a, int
         const uint4 lw = __ldg(reinterpret_cast<const uint4*>(clBase + (size_t)y * a.cenStride));
         const uint32_t Lw[4] = {lw.x, lw.y, lw.z, lw.w};
         // S[k] = shifted right census word (x0 - 16*lane - 16 + k), k = 0..19; cell (x0+c, j) uses S[16 + c - j]
+        // (prefetching the next row in registers was measured: 119 registers, 20 % slower - four independent
+        // columns per lane already provide the instruction-level parallelism, occupancy matters more here)
         uint32_t S[20];
         {
             const uint4* src = reinterpret_cast<const uint4*>(crBase + (size_t)y * a.cenStride);
@@ -384,7 +403,9 @@ static void launch_paths_D(cartb200_ctx* c, PathArgs a, int n, int p0, int p1, c
         a.vol2 = pair ? c->volumes + (size_t)(p + 1) * c->volPathStride : nullptr;
         if (a.dy == 0) {
             dim3 grid(ceilDiv(a.H, kHorizThreads / (D / 16)), n, pair ? 2 : 1);
-            aggregate_horizontal_kernel<D, kHorizU><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0);
+            // measured (B200, 64-frame batch): 8-pixel window with the next chunk prefetched at 5 CTAs/SM beats the
+            // variants tuned for occupancy (64 registers, 8 CTAs/SM) by 9 % - the kernel is pipe-bound, not latency-bound
+            aggregate_horizontal_kernel<D, kHorizU, true, 5><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0);
         } else if (a.dx == 0) {
             dim3 grid(ceilDiv(ceilDiv(a.W, 4), GPB), n, pair ? 2 : 1);
             aggregate_vertical_kernel<D><<<grid, 128, 0, s>>>(a, a.dy, pair ? 1 : 0);
