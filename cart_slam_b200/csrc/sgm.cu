@@ -9,6 +9,8 @@
 // Arithmetic: path costs are <= 31 + P2 (u8 in memory); inside the kernels two disparities share a
 // register as u16x2 and the recurrence runs on the DPX/video integer instructions of sm_90+/sm_100
 // (VIADDMNMX.U16x2, VIMNMX.U16x2, VIMNMX3) - no tensor cores: nothing here is a dense contraction.
+#include <cuda_pipeline.h>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -498,11 +500,13 @@ __device__ __forceinline__ void top2_of16(const uint32_t (&k)[16], uint32_t& b1,
     b2 = hi[0];
 }
 
+constexpr int kWtaDepth = 4;  // must divide 16 (the stage index is t % kWtaDepth inside the 16-step unrolled body)  // pixels in flight per lane (cp.async ring)
 template <int D, int P>
-__global__ void __launch_bounds__(128) wta_walk_kernel(WtaArgs a) {
+__global__ void __launch_bounds__(128, 5) wta_walk_kernel(WtaArgs a) {
     constexpr int LPP = D / 16;
     constexpr int GPB = 128 / LPP;
     __shared__ __align__(16) uint16_t stash[2][GPB][D];
+    extern __shared__ uint4 ring[];  // [kWtaDepth][P][128]
     const int lane = threadIdx.x % LPP, grp = threadIdx.x / LPP;
     const int item = blockIdx.x * GPB + grp;
     const bool live = item < a.nItems;
@@ -532,11 +536,16 @@ __global__ void __launch_bounds__(128) wta_walk_kernel(WtaArgs a) {
     uint32_t RM[16];  // running minima; logical slot j (disparity dbase + j) at step t lives in RM[(j - t) & 15]
 #pragma unroll
     for (int j = 0; j < 16; ++j) RM[j] = kKeyInf;
-    uint4 va[P], vb[P];  // two pixels in flight
+    // The volume vectors are staged through a per-thread shared-memory ring with cp.async (LDGSTS): kWtaDepth
+    // pixels in flight per lane without holding them in registers.  Every thread only reads back the 16-byte
+    // pieces it copied itself, so the only synchronisation is the thread's own cp.async wait.
+    uint4* ringT = ring + threadIdx.x;  // slot (stage, path) at ringT[(stage * P + path) * 128]
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-        va[p] = __ldg(reinterpret_cast<const uint4*>(vp + (size_t)p * a.volPathStride));
-        vb[p] = __ldg(reinterpret_cast<const uint4*>(vp + (size_t)p * a.volPathStride + D));
+    for (int st = 0; st < kWtaDepth; ++st) {
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+            __pipeline_memcpy_async(ringT + (st * P + p) * 128, vp + (size_t)p * a.volPathStride + st * D, 16);
+        __pipeline_commit();
     }
 
     for (int t0 = 0; t0 < T; t0 += 16, vp += 16 * D) {
@@ -545,7 +554,10 @@ __global__ void __launch_bounds__(128) wta_walk_kernel(WtaArgs a) {
         for (int t = 0; t < 16; ++t) {
             const int x = x0 + t0 + t;
             const bool act = x < x1;
-            uint4(&v)[P] = (t & 1) ? vb : va;
+            __pipeline_wait_prior(kWtaDepth - 1);  // the oldest stage (this pixel) has landed
+            uint4 v[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) v[p] = ringT[((t % kWtaDepth) * P + p) * 128];
             // ---- sum of the P path costs, u16x2 (d, d+1) in natural order ----
             uint32_t S[8];
 #pragma unroll
@@ -562,8 +574,10 @@ __global__ void __launch_bounds__(128) wta_walk_kernel(WtaArgs a) {
                 S[7] += __byte_perm(v[p].w, 0, 0x4342);
             }
 #pragma unroll
-            for (int p = 0; p < P; ++p)  // refill this buffer with the pixel two steps ahead
-                v[p] = __ldg(reinterpret_cast<const uint4*>(vp + (size_t)p * a.volPathStride + (t + 2) * D));
+            for (int p = 0; p < P; ++p)  // refill this stage with the pixel kWtaDepth steps ahead
+                __pipeline_memcpy_async(ringT + ((t % kWtaDepth) * P + p) * 128,
+                                        vp + (size_t)p * a.volPathStride + (t + kWtaDepth) * D, 16);
+            __pipeline_commit();
             if (!blockActive) {  // warp-uniform: only the ragged tail of a segment takes this path
                 const uint32_t mask = act ? 0u : 0x7FFF7FFFu;  // inactive steps lose against every real candidate
 #pragma unroll
@@ -641,10 +655,23 @@ static int launch_wta_D(cartb200_ctx* c, WtaArgs& a, int n, cudaStream_t s) {
     a.nItems = (int)(rows * a.nSeg);
     CB_CHECK_CUDA(c, cudaMemsetAsync(c->wtaR, 0xFF, (size_t)n * c->H * c->rkPitch * sizeof(uint32_t), s));
     dim3 grid(ceilDiv(a.nItems, GPB));
-    if (c->P == 4)
-        wta_walk_kernel<D, 4><<<grid, 128, 0, s>>>(a);
-    else
-        wta_walk_kernel<D, 8><<<grid, 128, 0, s>>>(a);
+    if (c->P == 4) {
+        static bool attr4 = false;
+        if (!attr4) {
+            cudaFuncSetAttribute(wta_walk_kernel<D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kWtaDepth * 4 * 128 * sizeof(uint4)));
+            attr4 = true;
+        }
+        wta_walk_kernel<D, 4><<<grid, 128, kWtaDepth * 4 * 128 * sizeof(uint4), s>>>(a);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(wta_walk_kernel<D, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kWtaDepth * 8 * 128 * sizeof(uint4)));
+            attr = true;
+        }
+        wta_walk_kernel<D, 8><<<grid, 128, kWtaDepth * 8 * 128 * sizeof(uint4), s>>>(a);
+    }
     CB_LAUNCH_CHECK(c);
     return CARTB200_OK;
 }
