@@ -391,6 +391,86 @@ __global__ void __launch_bounds__(128) aggregate_path_kernel(PathArgs a) {
     }
 }
 
+// ---- diagonals (MODE_HH only) -------------------------------------------------------------------------
+// A diagonal path (dx, dy = +-1) is vertical in the skewed coordinate u = x - dx * step (step = rows walked
+// from the starting edge): the kernel is the 4-columns-per-group vertical sweep over the W + H - 1 skewed
+// columns.  u0 and the row loop are multiples of 4, so inside a 4-fold unrolled row loop the position of the
+// group's first pixel inside a 16-byte aligned census window is static: census rows are still read with
+// aligned 16-byte loads (2 + 6 per row instead of 1 + 5).  Pixels outside the image get cost 0 through the
+// third input of the XOR's LOP3, which keeps the path state at zero until the path enters the image
+// (oracle/sgm.cpp D4: diagonal paths start where they enter the image); only the stores are predicated.
+template <int D, int DX>
+__device__ __forceinline__ void diagonal_body(const PathArgs& a, int dy, uint8_t* __restrict__ volBase) {
+    constexpr int LPP = D / 16;
+    constexpr int GPB = 128 / LPP;
+    const int lane = threadIdx.x % LPP;
+    const int group = threadIdx.x / LPP;
+    const int f = blockIdx.y;
+    const int W = a.W, H = a.H;
+    const int off4 = DX > 0 ? ((H - 1 + 3) & ~3) : 0;  // u = x - DX * step spans [-(H-1), W-1] (DX > 0) or [0, W+H-2]
+    const int nQuads = (W + off4 + (DX < 0 ? H - 1 : 0) + 3) >> 2;
+    int quad = blockIdx.x * GPB + group;
+    const bool valid = quad < nQuads;
+    if (!valid) quad = nQuads - 1;
+    const int u0 = 4 * quad - off4;
+    const uint32_t* clF = a.cenL + (size_t)f * a.cenFrameStride + a.cenMargin;
+    const uint32_t* crF = a.cenR + (size_t)f * a.cenFrameStride + a.cenMargin - 16 * lane - 16;
+    uint8_t* vF = volBase + (size_t)f * a.volFrameStride + 16 * lane;
+    const uint32_t P1v = pack16(a.P1, a.P1), P2v = pack16(a.P2, a.P2);
+
+    uint32_t dp[4][8];
+    uint32_t m[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        m[c] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dp[c][i] = 0;
+    }
+    for (int s4 = 0; s4 < H; s4 += 4) {
+        const int base4 = u0 + DX * s4;  // multiple of 4
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int step = s4 + r;
+            if (step >= H) break;  // uniform
+            const int y = dy > 0 ? step : H - 1 - step;
+            const int x0 = base4 + DX * r;                                   // pixel of column 0
+            const int o = DX > 0 ? r : (r == 0 ? 0 : 4 - r);                 // its position in the aligned window (static)
+            int wb = DX > 0 ? base4 : (r == 0 ? base4 : base4 - 4);          // aligned window start
+            const bool any = x0 + 3 >= 0 && x0 < W;
+            // groups that are completely outside read the zero margin in front of the row (costs are masked anyway)
+            if (!any) wb = -8;
+            const uint32_t* clRow = clF + (size_t)y * a.cenStride + wb;
+            const uint32_t* crRow = crF + (size_t)y * a.cenStride + wb;
+            uint32_t Lq[8], Sq[24];
+            load_words<8>(Lq, clRow);
+            load_words<24>(Sq, crRow);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int x = x0 + c;
+                const bool act = valid && x >= 0 && x < W;
+                const uint32_t mask = act ? 0xFFFFFFFFu : 0u;
+                uint32_t cost[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) cost[k] = __popc((Lq[o + c] ^ Sq[o + 16 + c - k]) & mask);
+                m[c] = group_min<LPP>(dp_step<LPP>(dp[c], cost, m[c], lane, P1v, P2v));
+                if (act) store_dp(vF + ((size_t)y * W + x) * D, dp[c]);
+            }
+        }
+    }
+}
+
+// blockIdx.z selects one of up to four diagonal paths (paths 4..7: (1,1), (-1,1), (1,-1), (-1,-1)) of one launch
+template <int D>
+__global__ void __launch_bounds__(128) aggregate_diagonal_kernel(PathArgs a, int firstPath, size_t volPathStride) {
+    const int p = firstPath + blockIdx.z;  // 4..7
+    const int dx = (p & 1) ? -1 : 1, dy = (p & 2) ? -1 : 1;
+    uint8_t* vol = a.vol + (size_t)blockIdx.z * volPathStride;
+    if (dx > 0)
+        diagonal_body<D, 1>(a, dy, vol);
+    else
+        diagonal_body<D, -1>(a, dy, vol);
+}
+
 static const int kDirs[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}};
 
 template <int D>
@@ -411,9 +491,17 @@ static void launch_paths_D(cartb200_ctx* c, PathArgs a, int n, int p0, int p1, c
         } else if (a.dx == 0) {
             dim3 grid(ceilDiv(ceilDiv(a.W, 4), GPB), n, pair ? 2 : 1);
             aggregate_vertical_kernel<D><<<grid, 128, 0, s>>>(a, a.dy, pair ? 1 : 0);
-        } else {
+        } else if (getenv("CARTB200_GENERIC_DIAGONALS")) {  // the first, generic formulation (kept for cross-checks)
             dim3 grid(ceilDiv(a.W + a.H - 1, GPB), n);
             aggregate_path_kernel<D><<<grid, 128, 0, s>>>(a);
+        } else {
+            // all remaining diagonals of the requested range share one launch
+            const int nz = p1 - p;
+            const int nQuads = (a.W + ((a.H - 1 + 3) & ~3) + 3) >> 2;  // the larger of the two skew directions
+            dim3 grid(ceilDiv(nQuads, GPB), n, nz);
+            aggregate_diagonal_kernel<D><<<grid, 128, 0, s>>>(a, p, c->volPathStride);
+            c->launches++;
+            break;
         }
         c->launches++;
         if (pair) ++p;
