@@ -83,6 +83,7 @@ def _load():
     lib.cartb200_interpolate.argtypes = [vp, i, vp, sz, sz, i, i, i, i, vp]
     lib.cartb200_sgm_intermediate.argtypes = [vp, i, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
     lib.cartb200_derivative.argtypes = [vp, i, vp, sz, sz, vp, sz, sz, vp, vp]
+    lib.cartb200_depth.argtypes = [vp, i, vp, sz, sz, vp, vp, sz, sz, vp]
     lib.cartb200_naive_derivative.argtypes = [vp, i, vp, sz, sz, vp, sz, sz, vp, vp]
     lib.cartb200_classify.argtypes = [vp, i, vp, sz, sz, i, i, vp, vp, sz, sz, vp]
     lib.cartb200_superpixels_reset.argtypes = [vp, i, vp, C.POINTER(i), vp]
@@ -106,7 +107,7 @@ EXPORTED_SYMBOLS = [
     "cartb200_default_config", "cartb200_create", "cartb200_destroy", "cartb200_last_error", "cartb200_version",
     "cartb200_launch_count", "cartb200_scratch_bytes", "cartb200_disparity", "cartb200_sgm_gray_census",
     "cartb200_sgm_aggregate", "cartb200_sgm_aggregate_path", "cartb200_sgm_wta_post", "cartb200_interpolate", "cartb200_sgm_intermediate",
-    "cartb200_derivative", "cartb200_naive_derivative", "cartb200_classify", "cartb200_superpixels_reset",
+    "cartb200_derivative", "cartb200_depth", "cartb200_naive_derivative", "cartb200_classify", "cartb200_superpixels_reset",
     "cartb200_superpixels_relax", "cartb200_superpixels_set_labels", "cartb200_superpixels_border_map",
     "cartb200_sp_planeseg", "cartb200_histogram_peak_update", "cartb200_default_sequence_opts",
     "cartb200_run_sequence_host", "cartb200_run_sequence_device", "cartb200_debug_ref_tile_i32",
@@ -331,6 +332,16 @@ class Context:
         self._check(_lib.cartb200_derivative(self._h, n, p, pitch, fs, deriv.data_ptr(), self.W * 4,
                                              self.W * self.H * 4, hist.data_ptr(), self._stream()))
         return deriv, hist
+
+    def depth(self, disp, Q):
+        """DepthModule: disparity [n,H,W] int16 (x16) -> XYZ float32 [n,H,W,3]; Q = 4x4 reprojection matrix."""
+        torch = self.torch
+        n, p, pitch, fs = self._img(disp, torch.int16)
+        q = np.ascontiguousarray(np.asarray(Q, np.float32).reshape(16))
+        xyz = torch.empty((n, self.H, self.W, 3), dtype=torch.float32, device=disp.device)
+        self._check(_lib.cartb200_depth(self._h, n, p, pitch, fs, q.ctypes.data, xyz.data_ptr(), self.W * 12,
+                                        self.W * self.H * 12, self._stream()))
+        return xyz
 
     def naive_derivative(self, disp):
         torch = self.torch

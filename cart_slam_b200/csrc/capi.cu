@@ -492,6 +492,17 @@ int cartb200_sp_planeseg(cartb200_ctx* c, int n, const int16_t* d, size_t dp, si
                               (cudaStream_t)stream);
 }
 
+int cartb200_depth(cartb200_ctx* c, int n, const int16_t* d, size_t dp, size_t dfs, const float* q16Host, float* xyz, size_t xp,
+                   size_t xfs, void* stream) {
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    if (!d || !xyz || !q16Host || dp < (size_t)c->W * 2 || xp < (size_t)c->W * 12 || (xp & 3)) {
+        c->err = "depth: bad arguments (depth pitch must be a multiple of 4 and hold 3 floats per pixel)";
+        return CARTB200_E_ARG;
+    }
+    return launch_depth(c, n, ImgBatch<const int16_t>{d, dp, dfs}, ImgBatch<float>{xyz, xp, xfs}, q16Host, (cudaStream_t)stream);
+}
+
 int cartb200_histogram_peak_update(const int32_t* hist, int32_t* params) {
     if (!hist || !params) return CARTB200_E_ARG;
     return cb::histogram_peak_update(hist, params);

@@ -124,6 +124,7 @@ int launch_classify(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, int c
 int launch_sp_planeseg(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, ImgBatch<const uint16_t> labels, int maxLabel, const int32_t* paramsDev, ImgBatch<uint8_t> unsm, ImgBatch<uint8_t> planes, cudaStream_t s);
 int launch_sp_reset(cartb200_ctx* c, int n, const int* slotsDev, cudaStream_t s);
 int launch_sp_relax(cartb200_ctx* c, int n, const int* slotsDev, int iterations, ImgBatch<const uint8_t> left, ImgBatch<const int16_t> deriv, bool hasDeriv, ImgBatch<uint16_t> out, cudaStream_t s);
+int launch_depth(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<float> xyz, const float* q16Host, cudaStream_t s);
 int launch_border_map(cartb200_ctx* c, Img<const uint16_t> labels, Img<uint8_t> border, cudaStream_t s);
 void build_sp_tile_tables(int W, int H, std::vector<int>& tileMap, std::vector<uint32_t>& tab);
 }  // namespace cb

@@ -312,4 +312,36 @@ int launch_sp_planeseg(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, Im
     return CARTB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// DepthModule::runInternal, /root/reference/src/modules/depth.cpp:9-25: disparity * (1/16) as float, then the
+// third-party cv::cuda::reprojectImageTo3D(Q, 3 channels).  Normative arithmetic: oracle/stages.cpp orc_depth
+// (single precision, same operation order; compiled without FMA contraction).  12 B written per pixel: HBM-bound.
+struct QMat {
+    float q[16];
+};
+
+__global__ void __launch_bounds__(256) depth_kernel(ImgBatch<const int16_t> disp, ImgBatch<float> xyz, QMat Q, int W, int H) {
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const float d = (float)__ldg(disp.frame(f).row(y) + x) * (1.0f / 16.0f);
+    const float fx = (float)x, fy = (float)y;
+    const float qx = fx * Q.q[0] + fy * Q.q[1] + Q.q[3], qy = fx * Q.q[4] + fy * Q.q[5] + Q.q[7];
+    const float qz = fx * Q.q[8] + fy * Q.q[9] + Q.q[11], qw = fx * Q.q[12] + fy * Q.q[13] + Q.q[15];
+    const float iW = 1.0f / (qw + Q.q[14] * d);
+    float* o = xyz.frame(f).row(y) + 3 * (size_t)x;
+    o[0] = (qx + Q.q[2] * d) * iW;
+    o[1] = (qy + Q.q[6] * d) * iW;
+    o[2] = (qz + Q.q[10] * d) * iW;
+}
+
+int launch_depth(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<float> xyz, const float* q16Host, cudaStream_t s) {
+    QMat Q;
+    for (int i = 0; i < 16; ++i) Q.q[i] = q16Host[i];
+    dim3 grid(ceilDiv(c->W, 256), c->H, n);
+    depth_kernel<<<grid, 256, 0, s>>>(disp, xyz, Q, c->W, c->H);
+    CB_LAUNCH_CHECK(c);
+    return CARTB200_OK;
+}
+
 }  // namespace cb

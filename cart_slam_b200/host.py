@@ -24,15 +24,19 @@ def _load():
     lib.cartb200_host_last_error.restype = C.c_char_p
     lib.cartb200_host_run_config.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cartb200_host_run_config_ex.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
 
 
 _lib = _load()
 
 
-def run_config(modules, left, right, skip_out_of_scope=False, sequential=True, want_labels=False, want_disparity=False):
+def run_config(modules, left, right, skip_out_of_scope=False, sequential=True, want_labels=False, want_disparity=False,
+               Q=None, want_depth=False):
     """Runs a reference-style module list (python list / JSON text) over host frames [n,H,W,3] uint8.
-    Returns dict(planes=..., labels=..., disparity=...)."""
+    Q: optional 4x4 reprojection matrix of the source (CameraIntrinsics::Q) for the "depth" module.
+    Returns dict(planes=..., labels=..., disparity=..., depth=...)."""
     text = modules if isinstance(modules, str) else json.dumps(modules)
     left = np.ascontiguousarray(left, dtype=np.uint8)
     right = np.ascontiguousarray(right, dtype=np.uint8)
@@ -40,10 +44,13 @@ def run_config(modules, left, right, skip_out_of_scope=False, sequential=True, w
     planes = np.full((n, H, W), 255, np.uint8)
     labels = np.zeros((n, H, W), np.uint16) if want_labels else None
     disp = np.zeros((n, H, W), np.int16) if want_disparity else None
-    rc = _lib.cartb200_host_run_config(text.encode(), int(skip_out_of_scope), W, H, n, left.ctypes.data, right.ctypes.data,
-                                       int(sequential), planes.ctypes.data,
-                                       labels.ctypes.data if labels is not None else None,
-                                       disp.ctypes.data if disp is not None else None)
+    depth = np.zeros((n, H, W, 3), np.float32) if want_depth else None
+    q = np.ascontiguousarray(np.asarray(Q, np.float32).reshape(16)) if Q is not None else None
+    rc = _lib.cartb200_host_run_config_ex(text.encode(), int(skip_out_of_scope), W, H, n, left.ctypes.data, right.ctypes.data,
+                                          int(sequential), q.ctypes.data if q is not None else None, planes.ctypes.data,
+                                          labels.ctypes.data if labels is not None else None,
+                                          disp.ctypes.data if disp is not None else None,
+                                          depth.ctypes.data if depth is not None else None)
     if rc != 0:
         raise HostError(_lib.cartb200_host_last_error().decode())
-    return dict(planes=planes, labels=labels, disparity=disp)
+    return dict(planes=planes, labels=labels, disparity=disp, depth=depth)

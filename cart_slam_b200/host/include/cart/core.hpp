@@ -35,7 +35,7 @@ void logMessage(const char* level, const std::string& who, const std::string& wh
 #define CART_LOG_ERROR(who, what) ::cart::logMessage("ERROR", (who), (what))
 
 // ---- device images -------------------------------------------------------------------------------
-enum ImageType { IMG_8UC1, IMG_8UC3, IMG_16SC1, IMG_16SC2, IMG_16UC1, IMG_32SC1, IMG_32SC2 };
+enum ImageType { IMG_8UC1, IMG_8UC3, IMG_16SC1, IMG_16SC2, IMG_16UC1, IMG_32SC1, IMG_32SC2, IMG_32FC3 };
 size_t imageElemBytes(ImageType t);
 
 struct Size {
@@ -146,9 +146,17 @@ class StereoDataElement : public DataElement {
 
 image_t getReferenceImage(std::shared_ptr<DataElement> element);
 
+// CameraIntrinsics (/root/reference/include/datasource.hpp:11-18): the 4x4 matrix OpenCV uses to reproject disparity
+// images into 3-D space, row-major floats.  Default: identity (the KITTI reader builds it at kitti.cpp:141-148).
+struct CameraIntrinsics {
+    float Q[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+};
+
 class DataSource {
    public:
     explicit DataSource(Size imageSize) : imageSize(imageSize) {}
+    const CameraIntrinsics getCameraIntrinsics() const { return intrinsics; }
+    void setCameraIntrinsics(const CameraIntrinsics& in) { intrinsics = in; }
     virtual ~DataSource() = default;
     std::shared_ptr<DataElement> getNext(void* stream);
     virtual bool isNextReady() = 0;
@@ -159,6 +167,7 @@ class DataSource {
    protected:
     virtual std::shared_ptr<DataElement> getNextInternal(void* stream) = 0;
     Size imageSize;
+    CameraIntrinsics intrinsics;
 };
 
 // Frames handed over in host memory (tightly packed BGR); replaces the KITTI/ZED readers for the bar.

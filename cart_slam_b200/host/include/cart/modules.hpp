@@ -2,6 +2,7 @@
 // each one a thin host shell around the cartb200 C ABI (include/cartb200.h):
 //   ImageDisparityModule                          /root/reference/include/modules/disparity.hpp:24-44
 //   ImageDisparityDerivativeModule                /root/reference/include/modules/disparity.hpp:70-79
+//   DepthModule                                   /root/reference/include/modules/depth.hpp:12-20
 //   SuperPixelModule                              /root/reference/include/modules/superpixels.hpp:15-41
 //   PlaneParameters / providers                   /root/reference/include/modules/planeseg.hpp:25-113
 //   DisparityPlaneSegmentationModule              /root/reference/include/modules/planeseg.hpp:115-162
@@ -17,6 +18,7 @@ struct cartb200_ctx;
 #define CARTSLAM_KEY_DISPARITY "disparity"
 #define CARTSLAM_KEY_DISPARITY_DERIVATIVE "disparity_derivative"
 #define CARTSLAM_KEY_DISPARITY_DERIVATIVE_HISTOGRAM "disparity_derivative_histogram"
+#define CARTSLAM_KEY_DEPTH "depth"
 #define CARTSLAM_KEY_SUPERPIXELS "superpixels"
 #define CARTSLAM_KEY_SUPERPIXELS_MAX_LABEL "superpixels_max_label"
 #define CARTSLAM_KEY_PLANES "planes"
@@ -64,6 +66,17 @@ class ImageDisparityModule : public SyncWrapperSystemModule {
 class ImageDisparityDerivativeModule : public SyncWrapperSystemModule {
    public:
     ImageDisparityDerivativeModule();
+    system_data_t runInternal(System& system, SystemRunData& data) override;
+
+   private:
+    std::unique_ptr<Kernels> kernels;  // created lazily: the image size is only known from the data
+};
+
+// DepthModule (/root/reference/include/modules/depth.hpp:12-20, src/modules/depth.cpp:9-25): "disparity" ->
+// "depth" (CV_32FC3 X, Y, Z) with the data source's reprojection matrix Q.
+class DepthModule : public SyncWrapperSystemModule {
+   public:
+    DepthModule();
     system_data_t runInternal(System& system, SystemRunData& data) override;
 
    private:

@@ -29,12 +29,30 @@ const char* cartb200_host_last_error() { return g_error.c_str(); }
 // 0: up to CARTSLAM_CONCURRENT_RUN_LIMIT frames in flight like the reference's main loop.
 // planes_out: n x H x W u8 (key "planes"); labels_out (nullable): n x H x W u16 (key "superpixels");
 // disparity_out (nullable): n x H x W s16.
+// q16 (nullable): row-major 4x4 reprojection matrix of the source (CameraIntrinsics::Q); depth_out (nullable):
+// n x H x W x 3 float (key "depth").
+int cartb200_host_run_config_ex(const char* modules_json, int skip_out_of_scope, int width, int height, int n,
+                                const uint8_t* left_bgr, const uint8_t* right_bgr, int sequential, const float* q16,
+                                uint8_t* planes_out, uint16_t* labels_out, int16_t* disparity_out, float* depth_out);
+
 int cartb200_host_run_config(const char* modules_json, int skip_out_of_scope, int width, int height, int n,
                              const uint8_t* left_bgr, const uint8_t* right_bgr, int sequential, uint8_t* planes_out,
                              uint16_t* labels_out, int16_t* disparity_out) {
+    return cartb200_host_run_config_ex(modules_json, skip_out_of_scope, width, height, n, left_bgr, right_bgr, sequential,
+                                       nullptr, planes_out, labels_out, disparity_out, nullptr);
+}
+
+int cartb200_host_run_config_ex(const char* modules_json, int skip_out_of_scope, int width, int height, int n,
+                                const uint8_t* left_bgr, const uint8_t* right_bgr, int sequential, const float* q16,
+                                uint8_t* planes_out, uint16_t* labels_out, int16_t* disparity_out, float* depth_out) {
     using namespace cart;
     try {
         auto source = std::make_shared<MemoryDataSource>(Size(width, height), n, left_bgr, right_bgr);
+        if (q16) {
+            CameraIntrinsics in;
+            std::memcpy(in.Q, q16, sizeof(in.Q));
+            source->setCameraIntrinsics(in);
+        }
         auto system = std::make_shared<System>(source);
         config::applyModuleConfigText(modules_json, system, skip_out_of_scope != 0);
         const size_t px = (size_t)width * height;
@@ -50,6 +68,8 @@ int cartb200_host_run_config(const char* modules_json, int skip_out_of_scope, in
                 run->getData<image_t>(CARTSLAM_KEY_SUPERPIXELS)->download(labels_out + px * (fid - 1), (size_t)width * 2);
             if (disparity_out && run->hasData(CARTSLAM_KEY_DISPARITY))
                 run->getData<image_t>(CARTSLAM_KEY_DISPARITY)->download(disparity_out + px * (fid - 1), (size_t)width * 2);
+            if (depth_out && run->hasData(CARTSLAM_KEY_DEPTH))
+                run->getData<image_t>(CARTSLAM_KEY_DEPTH)->download(depth_out + px * 3 * (fid - 1), (size_t)width * 12);
         };
         uint32_t id = 0;
         while (!source->isFinished()) {

@@ -39,7 +39,7 @@ std::shared_ptr<PlaneParameterProvider> readParameterProvider(const json& data) 
 
 // module types of the reference that are outside the hot-path scope
 const std::set<std::string> kOutOfScope = {
-    "superpixels_visualization", "depth", "depth_visualization", "zed_disparity", "disparity_visualization",
+    "superpixels_visualization", "depth_visualization", "zed_disparity", "disparity_visualization",
     "disparity_derivative_visualization", "features", "features_visualization", "optflow", "optflow_visualization",
     "planefit", "planecluster", "planefit_visualization", "disparity_planeseg_visualization", "bev_planeseg_visualization"};
 }  // namespace
@@ -63,6 +63,8 @@ void applyModuleConfigText(const std::string& text, std::shared_ptr<System> syst
                                                     get(m, "smoothing_radius", -1), get(m, "smoothing_iterations", 5));
         } else if (type == "disparity_derivative") {
             system->addModule<ImageDisparityDerivativeModule>();
+        } else if (type == "depth") {
+            system->addModule<DepthModule>();
         } else if (type == "disparity_planeseg" || type == "superpixel_disparity_planeseg") {
             auto provider = readParameterProvider(m.at("parameter_provider"));
             bool temporal = get(m, "use_temporal_smoothing", false);

@@ -33,6 +33,7 @@ size_t imageElemBytes(ImageType t) {
         case IMG_16UC1: return 2;
         case IMG_32SC1: return 4;
         case IMG_32SC2: return 8;
+        case IMG_32FC3: return 12;
     }
     return 1;
 }

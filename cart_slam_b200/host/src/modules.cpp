@@ -108,6 +108,33 @@ system_data_t ImageDisparityDerivativeModule::runInternal(System&, SystemRunData
                              MODULE_MAKE_PAIR(CARTSLAM_KEY_DISPARITY_DERIVATIVE_HISTOGRAM, image_t, histogram));
 }
 
+// ---- DepthModule (depth.cpp:9-25) -----------------------------------------------------------------------
+DepthModule::DepthModule() : SyncWrapperSystemModule("Depth") {
+    requiresData.push_back(module_dependency_t(CARTSLAM_KEY_DISPARITY));
+    providesData.push_back(CARTSLAM_KEY_DEPTH);
+}
+
+system_data_t DepthModule::runInternal(System& system, SystemRunData& data) {
+    auto disparity = data.getData<image_t>(CARTSLAM_KEY_DISPARITY);
+    if (disparity->empty() || disparity->type != IMG_16SC1) throw std::runtime_error("Disparity must be of type CV_16SC1");
+    const CameraIntrinsics in = system.getDataSource()->getCameraIntrinsics();
+    image_t depth(disparity->rows, disparity->cols, IMG_32FC3);
+    StreamGuard st;
+    {
+        static std::mutex createMutex;
+        std::lock_guard<std::mutex> lock(createMutex);
+        if (!kernels) kernels.reset(new Kernels(disparity->size(), false, false));
+    }
+    {
+        std::lock_guard<std::mutex> lock(kernels->mutex);
+        kernels->check(cartb200_depth(kernels->get(), 1, disparity->as<int16_t>(), disparity->pitch, 0, in.Q, depth.as<float>(),
+                                      depth.pitch, 0, st.s),
+                       "DepthModule");
+        st.sync();
+    }
+    return MODULE_RETURN_SHARED(CARTSLAM_KEY_DEPTH, image_t, depth);
+}
+
 // ---- SuperPixelModule (superpixels.cu:19-121) -----------------------------------------------------------
 SuperPixelModule::SuperPixelModule(const Size imageRes, const unsigned int initialIterations, const unsigned int iterations,
                                    const unsigned int blockSize, const unsigned int resetIterations, const double directCliqueCost,

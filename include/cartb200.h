@@ -167,6 +167,15 @@ int cartb200_sp_planeseg(cartb200_ctx* ctx, int n, const int16_t* derivative, si
                          uint8_t* planes_unsmoothed, uint8_t* planes, size_t planes_pitch, size_t planes_frame_stride,
                          void* stream);
 
+/* ---- depth (the stage right after disparity) ------------------------------
+ * Replaces DepthModule::runInternal (/root/reference/src/modules/depth.cpp:9-25): convertTo(CV_32F, 1/16) +
+ * cv::cuda::reprojectImageTo3D(disparityFloat, depth, Q, 3).  q16_host: the 4x4 reprojection matrix Q
+ * (CameraIntrinsics::Q, /root/reference/include/datasource.hpp:11-18; built at src/sources/kitti.cpp:141-148),
+ * row-major floats on the HOST.  depth: n frames of CV_32FC3 (X, Y, Z), "depth" key.  Invalid disparities are
+ * not treated specially (neither does the reference's GPU path). */
+int cartb200_depth(cartb200_ctx* ctx, int n, const int16_t* disparity, size_t disp_pitch, size_t disp_frame_stride,
+                   const float* q16_host, float* depth, size_t depth_pitch, size_t depth_frame_stride, void* stream);
+
 /* ---- host-side parameter estimation --------------------------------------------------------------
  * HistogramPeakPlaneParameterProvider::updatePlaneParameters (/root/reference/src/modules/planeseg/planeseg.cu:405-458)
  * + util::findPeaks (/root/reference/src/utils/peaks.cpp:12-72).  hist256: HOST 256 x int32.

@@ -29,6 +29,8 @@ int orc_naive_derivative(const int16_t* disp, int W, int H, int16_t* deriv, int3
 int orc_classify(const int16_t* deriv, long n, int stride, int hS, int hE, int vS, int vE, uint8_t* planes);
 int orc_sp_planeseg(const int16_t* deriv2, const uint16_t* labels, int W, int H, int maxLabel, int hS, int hE, int vS,
                     int vE, uint8_t* planesUnsmoothed, uint8_t* planes);
+/* depth: DepthModule (src/modules/depth.cpp:9-25): convertTo(CV_32F, 1/16) + cv::cuda::reprojectImageTo3D(Q), 3 channels */
+int orc_depth(const int16_t* disp, int W, int H, const float* Q16, float* xyz);
 int orc_find_peaks(const int32_t* hist, int n, int* out, int maxPeaks);
 int orc_histogram_peak_update(const int32_t* hist, int* params);
 int orc_block_init(int W, int H, int bw, int bh, uint16_t* labels);

@@ -138,6 +138,16 @@ def derivative(disp, want_mask=False):
     return (out, hist, m) if want_mask else (out, hist)
 
 
+def depth(disp, Q):
+    """DepthModule: disparity (x16 fixed point) -> XYZ float32 [H, W, 3] with the 4x4 reprojection matrix Q."""
+    disp = _c(disp, np.int16)
+    H, W = disp.shape
+    q = _c(np.asarray(Q, np.float32).reshape(16), np.float32)
+    out = np.empty((H, W, 3), np.float32)
+    lib().orc_depth(_p(disp), W, H, _p(q), _p(out))
+    return out
+
+
 def naive_derivative(disp, want_mask=False):
     disp = _c(disp, np.int16)
     H, W = disp.shape

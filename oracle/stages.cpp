@@ -302,4 +302,27 @@ int orc_histogram_peak_update(const int32_t* hist, int* params) {
     return 1;
 }
 
+
+// DepthModule::runInternal, /root/reference/src/modules/depth.cpp:9-25: disparity / 16 as float, then the
+// THIRD-PARTY cv::cuda::reprojectImageTo3D(disparityFloat, depth, Q, 3) (opencv_contrib cudastereo, absent from
+// /root/reference; recollection of its kernel: single precision, per pixel
+//   q* = x Q[*][0] + y Q[*][1] + Q[*][3];  iW = 1 / (qw + Q[3][2] d);  out = ((q* + Q[*][2] d) iW) for x, y, z,
+// no handling of invalid disparities).  Pinned within float tolerance against CPU cv2.reprojectImageTo3D
+// (tests/test_oracle_cpu.py) - the CPU version accumulates in double, hence a tolerance and not bit equality.
+int orc_depth(const int16_t* disp, int W, int H, const float* Q, float* xyz) {
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const float d = (float)disp[(size_t)y * W + x] * (1.0f / 16.0f);
+            const float fx = (float)x, fy = (float)y;
+            const float qx = fx * Q[0] + fy * Q[1] + Q[3], qy = fx * Q[4] + fy * Q[5] + Q[7];
+            const float qz = fx * Q[8] + fy * Q[9] + Q[11], qw = fx * Q[12] + fy * Q[13] + Q[15];
+            const float iW = 1.0f / (qw + Q[14] * d);
+            float* o = xyz + ((size_t)y * W + x) * 3;
+            o[0] = (qx + Q[2] * d) * iW;
+            o[1] = (qy + Q[6] * d) * iW;
+            o[2] = (qz + Q[10] * d) * iW;
+        }
+    return 0;
+}
+
 }  // extern "C"

@@ -273,3 +273,22 @@ def test_full_size_kitti_properties(gpu):
         lab0, nlab = po.block_init(W, H, 12, 12)
         o_lab, _, _ = po.sp_relax(lab0, nlab, po.ycrcb(L[0]), dv[0], 8)
         assert (host(labels)[0] == o_lab).mean() >= LABEL_AGREEMENT
+
+
+def test_depth_matches_oracle(gpu):
+    """DepthModule replacement: single-precision arithmetic in the oracle's order (no FMA contraction) - tolerance 1e-6
+    relative, and in practice bit-identical."""
+    W, H = 333, 97
+    rng = np.random.default_rng(3)
+    disp = rng.integers(-40, 120 * 16, (2, H, W)).astype(np.int16)
+    disp[0, 5:9, 7:30] = -32768  # invalid marker: no special handling, like the reference's GPU path
+    Q = np.eye(4, dtype=np.float32)
+    Q[0, 3], Q[1, 3], Q[2, 2], Q[2, 3], Q[3, 2], Q[3, 3] = -166.0, -48.5, 0, 718.9, -1 / 0.537, 0.25
+    cfg = cb.Config(W, H, max_batch=2, enable_sgm=False, enable_superpixels=False)
+    with cb.Context(cfg) as ctx:
+        xyz = host(ctx.depth(dev(disp), Q))
+    for f in range(2):
+        o = po.depth(disp[f], Q)
+        fin = np.isfinite(o)
+        assert np.array_equal(np.isfinite(xyz[f]), fin)
+        assert np.allclose(xyz[f][fin], o[fin], rtol=1e-6, atol=0)

@@ -28,7 +28,7 @@ def test_unknown_and_out_of_scope_modules_are_rejected():
     with pytest.raises(host.HostError, match="not an array"):
         host.run_config({"type": "disparity"}, L, L)
     with pytest.raises(host.HostError, match="No modules"):
-        host.run_config([{"type": "depth"}, {"type": "disparity_visualization"}], L, L, skip_out_of_scope=True)
+        host.run_config([{"type": "optflow"}, {"type": "disparity_visualization"}], L, L, skip_out_of_scope=True)
 
 
 def test_static_provider_requires_its_keys():
@@ -112,3 +112,22 @@ def test_superpixel_json_pipeline_matches_sequence_runner():
     assert np.array_equal(out["disparity"], disp)
     # same kernels, same order of operations per frame: the chunked runner and the frame-by-frame modules agree exactly
     assert np.array_equal(out["planes"], planes)
+
+
+@pytest.mark.gpu
+def test_depth_module_through_the_json_pipeline():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import pyoracle as po
+
+    W, H, D, n = 192, 96, 64, 3
+    L, R, fr = _frames(W, H, D, n)
+    Q = np.eye(4, dtype=np.float32)
+    Q[0, 3], Q[1, 3], Q[2, 2], Q[2, 3], Q[3, 2], Q[3, 3] = -96.0, -48.0, 0, 400.0, -2.0, 0.1
+    out = host.run_config([{"type": "disparity", "num_disparities": D, "smoothing_radius": 2, "smoothing_iterations": 1},
+                           {"type": "depth"}], L, R, Q=Q, want_depth=True, want_disparity=True)
+    for i in range(n):
+        o = po.depth(out["disparity"][i], Q)
+        fin = np.isfinite(o)
+        assert np.allclose(out["depth"][i][fin], o[fin], rtol=1e-6, atol=0)

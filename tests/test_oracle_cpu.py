@@ -267,3 +267,21 @@ def test_sp_planeseg_majority_rules():
     assert (po.sp_planeseg(deriv, labels, 2, 1, 30, -3, 1)[1][:, 4:] == 2).all()
     with pytest.raises(RuntimeError):
         po.sp_planeseg(deriv, labels, 6000, 1, 30, -3, 1)  # (maxLabel+1)*6 > 32768, sp_planeseg.cu:327-331
+
+
+def test_depth_oracle_matches_opencv_cpu():
+    """DepthModule (depth.cpp:9-25): the oracle's single-precision restatement of cv::cuda::reprojectImageTo3D is pinned
+    against CPU cv2.reprojectImageTo3D (which accumulates in double): relative tolerance 1e-5."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(7)
+    W, H = 320, 100
+    disp = rng.integers(5 * 16, 100 * 16, (H, W)).astype(np.int16)
+    Q = np.eye(4, dtype=np.float32)  # the KITTI reader's matrix (kitti.cpp:141-148)
+    Q[0, 3], Q[1, 3], Q[2, 2], Q[2, 3], Q[3, 2], Q[3, 3] = -160.5, -50.25, 0, 721.5, -1 / 0.54, 0.3
+    o = po.depth(disp, Q)
+    c = cv2.reprojectImageTo3D(disp.astype(np.float32) / 16.0, Q)
+    assert np.allclose(o, c, rtol=1e-5, atol=1e-5)
+    # known answer: Z = f / (-d / B + q33) on the optical axis
+    y, x = 50, 160
+    d = disp[y, x] / 16.0
+    assert abs(o[y, x, 2] - 721.5 / (-d / 0.54 + 0.3)) < 1e-3
