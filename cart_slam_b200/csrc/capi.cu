@@ -582,7 +582,7 @@ struct HostI32 {
 
 int32_t cartb200_debug_ref_tile_i32(const int32_t* img, int W, int H, int bx, int by, int bdx, int bdy, int XB, int YB,
                                     int yPad, int xPad, int interp, long alloc, int32_t undef, int lx, int ly) {
-    TileGeom g{W, H, bdx * XB, bdy * YB, xPad, yPad, XB, YB, alloc};
+    TileGeom g{W, H, bdx * XB, bdy * YB, xPad, yPad, XB, YB, (int)alloc};
     HostI32 acc{img, W};
     TileEval<int32_t, HostI32> te(acc, g, bx, by, undef);
     return interp ? te.value<true>(lx, ly) : te.value<false>(lx, ly);

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) interpolate_kernel(ImgBatch<const int16_t
     int16_t* cur = sm;
     int16_t* nxt = sm + N;
     const int bx = blockIdx.x, by = blockIdx.y, f = blockIdx.z;
-    TileGeom g{W, H, 64, 64, pad, pad, 4, 4, (long)N};
+    TileGeom g{W, H, 64, 64, pad, pad, 4, 4, N};
     DispAccessor acc{src.frame(f)};
     TileEval<int16_t, DispAccessor> te(acc, g, bx, by, kInvalid);
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128) derivative_kernel(ImgBatch<const int16_t>
     const int x = blockIdx.x * 128 + threadIdx.x;
     const int y0 = blockIdx.y * kDerivRows;
     if (x < W) {
-        TileGeom g{W, H, 128, 128, 2, 2, 4, 4, 132L * 132L};
+        TileGeom g{W, H, 128, 128, 2, 2, 4, 4, 132 * 132};
         DispAccessor acc{disp.frame(f)};
         const int bx = x >> 7, lx = x & 127;
         Img<int16_t> out = deriv.frame(f);
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(128) naive_derivative_kernel(ImgBatch<const in
     const int bandsPerTile = 128 / kNaiveRows;
     const int by = blockIdx.y / bandsPerTile, r0 = (blockIdx.y % bandsPerTile) * kNaiveRows;
     const int lx = threadIdx.x, x = bx * 128 + lx;
-    TileGeom g{W, H, 128, 128, 0, 2, 4, 4, 128L * 144L};
+    TileGeom g{W, H, 128, 128, 0, 2, 4, 4, 128 * 144};
     DispAccessor acc{disp.frame(f)};
     TileEval<int16_t, DispAccessor> te(acc, g, bx, by, kInvalid);
     for (int k = 0; k < kNaiveRows + 6; ++k) {

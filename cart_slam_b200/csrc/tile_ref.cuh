@@ -22,7 +22,7 @@ struct TileGeom {
     int tileW, tileH;  // blockDim * batch
     int xPad, yPad;    // halo (note the reference's argument order is (yPadding, xPadding), Q9)
     int XB, YB;        // per-thread batch (needed by the halo phases)
-    long alloc;        // elements of the shared array the reference kernel declares
+    int alloc;         // elements of the shared array the reference kernel declares
 };
 
 template <typename T, typename Img>
@@ -31,13 +31,13 @@ struct TileEval {
     const TileGeom& g;
     int bx, by;
     T undef;
-    long startX, startY;
+    int startX, startY;  // 32-bit throughout: images are < 65536 pixels per side (64-bit divisions are slow on the GPU)
     int pXS, pSXS, pYS, pSYS, xDim, yDim, S;
 
     CB_HD TileEval(const Img& img_, const TileGeom& g_, int bx_, int by_, T undef_)
         : img(img_), g(g_), bx(bx_), by(by_), undef(undef_) {
-        startX = (long)bx * g.tileW;
-        startY = (long)by * g.tileH;
+        startX = bx * g.tileW;
+        startY = by * g.tileH;
         pXS = (int)(startX - g.xPad > 0 ? startX - g.xPad : 0);
         pSXS = pXS - (int)startX;
         pYS = (int)(startY - g.yPad > 0 ? startY - g.yPad : 0);
@@ -48,28 +48,28 @@ struct TileEval {
         yDim = (int)(remH < fullH ? remH : fullH);
         S = g.tileW + 2 * g.xPad;
     }
-    CB_HD long index(int lx, int ly) const { return (long)(ly + g.yPad) * S + (lx + g.xPad); }
-    CB_HD T image(long x, long y) const {
+    CB_HD int index(int lx, int ly) const { return (ly + g.yPad) * S + (lx + g.xPad); }
+    CB_HD T image(int x, int y) const {
         if (x < 0 || x >= g.W || y < 0 || y >= g.H) return undef;
-        return img((int)x, (int)y);
+        return img(x, y);
     }
     // value after the body copy only (cuda.cuh:91-96)
-    CB_HD T body(long L) const {
-        const long rel = L - index(pSXS, pSYS);
+    CB_HD T body(int L) const {
+        const int rel = L - index(pSXS, pSYS);
         if (rel < 0) return undef;
-        const long i = rel / S, e = rel - i * S;
+        const int i = (int)((unsigned)rel / (unsigned)S), e = rel - i * S;
         if (i >= yDim || e >= xDim) return undef;
         return image(pXS + e, startY + i);
     }
     CB_HD T body_at(int lx, int ly) const {
-        const long L = index(lx, ly);
+        const int L = index(lx, ly);
         if (L < 0 || L >= g.alloc) return undef;
         return body(L);
     }
 
     template <bool Interp>
     CB_HD T value(int lx, int ly) const {
-        const long L = index(lx, ly);
+        const int L = index(lx, ly);
         if (L < 0 || L >= g.alloc) return undef;
         const bool top = (int)startY - g.yPad < 0;
         const bool bottom = startY + g.tileH + g.yPad > g.H;
@@ -105,14 +105,14 @@ struct TileEval {
             // bottom rows tileH+i <- image row H-1 (row copies, later i wins)  (cuda.cuh:125-127)
             if (bottom) {
                 for (int i = g.yPad - 1; i >= 0; --i) {
-                    const long rel = L - index(pSXS, g.tileH + i);
+                    const int rel = L - index(pSXS, g.tileH + i);
                     if (rel >= 0 && rel < xDim) return image(pXS + rel, g.H - 1);
                 }
             }
             // top rows -i <- image row 0  (cuda.cuh:103-105)
             if (top) {
                 for (int i = g.yPad; i >= 1; --i) {
-                    const long rel = L - index(pSXS, -i);
+                    const int rel = L - index(pSXS, -i);
                     if (rel >= 0 && rel < xDim) return image(pXS + rel, 0);
                 }
             }
