@@ -24,6 +24,9 @@ def _load():
     lib.cartb200_host_last_error.restype = C.c_char_p
     lib.cartb200_host_run_config.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cartb200_host_decode_png.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.cartb200_host_run_source.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cartb200_host_run_config_ex.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
@@ -54,3 +57,41 @@ def run_config(modules, left, right, skip_out_of_scope=False, sequential=True, w
     if rc != 0:
         raise HostError(_lib.cartb200_host_last_error().decode())
     return dict(planes=planes, labels=labels, disparity=disp, depth=depth)
+
+
+def decode_png(path):
+    """The source layer's PNG reader (replaces cv::imread in the KITTI source): returns BGR uint8 [H, W, 3]."""
+    w, h = C.c_int(), C.c_int()
+    if _lib.cartb200_host_decode_png(str(path).encode(), None, 0, C.byref(w), C.byref(h)) != 0:
+        raise HostError(_lib.cartb200_host_last_error().decode())
+    out = np.empty((h.value, w.value, 3), np.uint8)
+    if _lib.cartb200_host_decode_png(str(path).encode(), out.ctypes.data, out.nbytes, C.byref(w), C.byref(h)) != 0:
+        raise HostError(_lib.cartb200_host_last_error().decode())
+    return out
+
+
+def open_source(source):
+    """Builds a data source from a reference-style source config (dict / JSON text); returns (width, height, Q)."""
+    text = source if isinstance(source, str) else json.dumps(source)
+    w, h = C.c_int(), C.c_int()
+    q = np.zeros(16, np.float32)
+    if _lib.cartb200_host_run_source(text.encode(), None, 0, 0, C.byref(w), C.byref(h), q.ctypes.data, None, None, None) < 0:
+        raise HostError(_lib.cartb200_host_last_error().decode())
+    return w.value, h.value, q.reshape(4, 4)
+
+
+def run_source(source, modules, max_frames, skip_out_of_scope=False, want_disparity=False, want_depth=False):
+    """Runs a module list over the frames of an on-disk source (config/sources/*.json schema), in id order."""
+    W, H, Q = open_source(source)
+    stext = source if isinstance(source, str) else json.dumps(source)
+    mtext = modules if isinstance(modules, str) else json.dumps(modules)
+    planes = np.full((max_frames, H, W), 255, np.uint8)
+    disp = np.zeros((max_frames, H, W), np.int16) if want_disparity else None
+    depth = np.zeros((max_frames, H, W, 3), np.float32) if want_depth else None
+    w, h = C.c_int(), C.c_int()
+    n = _lib.cartb200_host_run_source(stext.encode(), mtext.encode(), int(skip_out_of_scope), max_frames, C.byref(w), C.byref(h),
+                                      None, planes.ctypes.data, disp.ctypes.data if disp is not None else None,
+                                      depth.ctypes.data if depth is not None else None)
+    if n < 0:
+        raise HostError(_lib.cartb200_host_last_error().decode())
+    return dict(n=n, Q=Q, planes=planes[:n], disparity=None if disp is None else disp[:n], depth=None if depth is None else depth[:n])

@@ -68,6 +68,7 @@ class DeviceImage {
     std::shared_ptr<Buf> buf;
 };
 typedef DeviceImage image_t;
+void syncStream(void* stream);  // cudaStreamSynchronize; throws std::runtime_error on failure
 
 // ---- data hand-off -------------------------------------------------------------------------------
 typedef std::pair<std::string, std::shared_ptr<void>> system_data_pair_t;

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "cart/modules.hpp"
+#include "cart/sources.hpp"
 
 namespace {
 std::string g_error;
@@ -79,6 +80,63 @@ int cartb200_host_run_config_ex(const char* modules_json, int skip_out_of_scope,
         }
         while (!inflight.empty()) collect();
         return 0;
+    } catch (const std::exception& e) {
+        g_error.clear();
+        describe(e, g_error);
+        return -1;
+    }
+}
+
+// Decodes a PNG to BGR with the source layer's reader (no GPU needed).  out may be NULL to query the size.
+int cartb200_host_decode_png(const char* path, uint8_t* out, size_t out_capacity, int* width, int* height) {
+    try {
+        std::vector<uint8_t> bgr;
+        int w = 0, h = 0;
+        cart::util::readPngBgr(path, bgr, w, h);
+        if (width) *width = w;
+        if (height) *height = h;
+        if (out) {
+            if (out_capacity < bgr.size()) throw std::runtime_error("output buffer too small");
+            std::memcpy(out, bgr.data(), bgr.size());
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_error.clear();
+        describe(e, g_error);
+        return -1;
+    }
+}
+
+// Builds the data source from a reference-style source config (config/sources/*.json), reports its image size and
+// reprojection matrix, and - when modules_json is given - runs the module list over at most max_frames frames.
+// Returns the number of frames processed (>= 0) or -1.  Output arrays hold max_frames frames.
+int cartb200_host_run_source(const char* source_json, const char* modules_json, int skip_out_of_scope, int max_frames,
+                             int* width, int* height, float* q16_out, uint8_t* planes_out, int16_t* disparity_out,
+                             float* depth_out) {
+    using namespace cart;
+    try {
+        auto source = config::createDataSourceFromText(source_json);
+        const Size size = source->getImageSize();
+        if (width) *width = size.width;
+        if (height) *height = size.height;
+        if (q16_out) std::memcpy(q16_out, source->getCameraIntrinsics().Q, 16 * sizeof(float));
+        if (!modules_json) return 0;
+        auto system = std::make_shared<System>(source);
+        config::applyModuleConfigText(modules_json, system, skip_out_of_scope != 0);
+        const size_t px = (size_t)size.width * size.height;
+        int done = 0;
+        while (done < max_frames && !source->isFinished()) {
+            system->run().get();  // in id order
+            ++done;
+            auto run = system->getRunById((uint32_t)done);
+            if (planes_out && run->hasData(CARTSLAM_KEY_PLANES))
+                run->getData<image_t>(CARTSLAM_KEY_PLANES)->download(planes_out + px * (done - 1), (size_t)size.width);
+            if (disparity_out && run->hasData(CARTSLAM_KEY_DISPARITY))
+                run->getData<image_t>(CARTSLAM_KEY_DISPARITY)->download(disparity_out + px * (done - 1), (size_t)size.width * 2);
+            if (depth_out && run->hasData(CARTSLAM_KEY_DEPTH))
+                run->getData<image_t>(CARTSLAM_KEY_DEPTH)->download(depth_out + px * 3 * (done - 1), (size_t)size.width * 12);
+        }
+        return done;
     } catch (const std::exception& e) {
         g_error.clear();
         describe(e, g_error);

@@ -7,6 +7,7 @@
 
 #include "../../../third_party/nlohmann/json.hpp"
 #include "cart/modules.hpp"
+#include "cart/sources.hpp"
 
 namespace cart::config {
 
@@ -94,6 +95,25 @@ void readModuleConfig(const std::string& path, std::shared_ptr<System> system, b
     std::stringstream ss;
     ss << file.rdbuf();
     applyModuleConfigText(ss.str(), system, skipOutOfScope);
+}
+
+// createDataSource, /root/reference/src/cartconfig.cpp:82-104
+std::shared_ptr<DataSource> createDataSourceFromText(const std::string& text) {
+    const json cfg = json::parse(text);
+    if (!cfg.is_object()) throw std::runtime_error("Data source configuration is not an object.");
+    const std::string sourcePath = cfg.at("path").get<std::string>();
+    const std::string type = cfg.at("type").get<std::string>();
+    if (type == "kitti") return std::make_shared<sources::KITTIDataSource>(sourcePath, get(cfg, "sequence", 0));
+    if (type == "zed") throw std::runtime_error("Data source type zed needs the proprietary ZED SDK (outside the scope of this build).");
+    throw std::runtime_error("Unknown data source type.");
+}
+
+std::shared_ptr<DataSource> readDataSourceConfig(const std::string& path) {
+    std::ifstream file(path);
+    if (!file.is_open()) throw std::runtime_error("Could not open file " + path);
+    std::stringstream ss;
+    ss << file.rdbuf();
+    return createDataSourceFromText(ss.str());
 }
 
 }  // namespace cart::config

@@ -147,6 +147,8 @@ image_t getReferenceImage(std::shared_ptr<DataElement> element) {
     }
 }
 
+void syncStream(void* stream) { cudaCheck(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize"); }
+
 std::shared_ptr<DataElement> DataSource::getNext(void* stream) {
     if (!isNextReady()) throw std::runtime_error("Next element is not ready!");
     auto element = getNextInternal(stream);

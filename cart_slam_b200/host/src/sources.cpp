@@ -1,0 +1,246 @@
+// KITTI odometry data source + PNG reader (see cart/sources.hpp for the reference files this follows).
+#include "cart/sources.hpp"
+
+#include <sys/stat.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+namespace cart {
+namespace util {
+
+std::string resolvePath(const std::string& path) {
+    if (!path.empty() && path[0] == '~') {
+        const char* home = getenv("HOME");
+        if (home) return std::string(home) + path.substr(1);
+    }
+    return path;
+}
+
+namespace {
+uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+int paeth(int a, int b, int c) {
+    const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+}  // namespace
+
+void readPngBgr(const std::string& path, std::vector<uint8_t>& bgr, int& width, int& height) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f.is_open()) throw std::runtime_error("Failed to open image " + path + ": " + strerror(errno));
+    std::vector<uint8_t> file((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    if (file.size() < 8 + 25 || std::memcmp(file.data(), sig, 8) != 0) throw std::runtime_error(path + ": not a PNG file");
+    int bitDepth = 0, colorType = 0, interlace = 0;
+    width = height = 0;
+    std::vector<uint8_t> idat, palette;
+    size_t pos = 8;
+    bool end = false;
+    while (!end && pos + 12 <= file.size()) {
+        const uint32_t len = be32(&file[pos]);
+        const char* type = reinterpret_cast<const char*>(&file[pos + 4]);
+        const uint8_t* data = &file[pos + 8];
+        if (pos + 12 + (size_t)len > file.size()) throw std::runtime_error(path + ": truncated PNG chunk");
+        if (!std::memcmp(type, "IHDR", 4)) {
+            if (len < 13) throw std::runtime_error(path + ": bad IHDR");
+            width = (int)be32(data);
+            height = (int)be32(data + 4);
+            bitDepth = data[8];
+            colorType = data[9];
+            interlace = data[12];
+        } else if (!std::memcmp(type, "PLTE", 4)) {
+            palette.assign(data, data + len);
+        } else if (!std::memcmp(type, "IDAT", 4)) {
+            idat.insert(idat.end(), data, data + len);
+        } else if (!std::memcmp(type, "IEND", 4)) {
+            end = true;
+        }
+        pos += 12 + (size_t)len;
+    }
+    if (width <= 0 || height <= 0 || width > 65535 || height > 65535) throw std::runtime_error(path + ": bad PNG size");
+    if (bitDepth != 8 || interlace != 0) throw std::runtime_error(path + ": only 8-bit non-interlaced PNG files are supported");
+    int ch;
+    switch (colorType) {
+        case 0: ch = 1; break;  // gray
+        case 2: ch = 3; break;  // RGB
+        case 3: ch = 1; break;  // palette
+        case 4: ch = 2; break;  // gray + alpha
+        case 6: ch = 4; break;  // RGBA
+        default: throw std::runtime_error(path + ": unsupported PNG colour type");
+    }
+    if (colorType == 3 && palette.size() < 3) throw std::runtime_error(path + ": palette image without PLTE");
+    const size_t stride = (size_t)width * ch;
+    std::vector<uint8_t> raw((stride + 1) * (size_t)height);
+    uLongf rawLen = (uLongf)raw.size();
+    if (uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size()) != Z_OK || rawLen != raw.size())
+        throw std::runtime_error(path + ": PNG inflate failed");
+    // undo the scanline filters in place
+    std::vector<uint8_t> prevRow(stride, 0);
+    bgr.resize((size_t)width * height * 3);
+    for (int y = 0; y < height; ++y) {
+        uint8_t* row = &raw[(stride + 1) * (size_t)y];
+        const int filter = row[0];
+        uint8_t* px = row + 1;
+        for (size_t i = 0; i < stride; ++i) {
+            const int a = i >= (size_t)ch ? px[i - ch] : 0, b = prevRow[i], c = i >= (size_t)ch ? prevRow[i - ch] : 0;
+            int v = px[i];
+            switch (filter) {
+                case 0: break;
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) >> 1; break;
+                case 4: v += paeth(a, b, c); break;
+                default: throw std::runtime_error(path + ": bad PNG filter");
+            }
+            px[i] = (uint8_t)v;
+        }
+        std::memcpy(prevRow.data(), px, stride);
+        uint8_t* out = &bgr[(size_t)y * width * 3];
+        for (int x = 0; x < width; ++x) {
+            uint8_t r, g, bl;
+            if (colorType == 0 || colorType == 4) {
+                r = g = bl = px[(size_t)x * ch];
+            } else if (colorType == 3) {
+                const size_t k = (size_t)px[x] * 3;
+                if (k + 2 >= palette.size()) throw std::runtime_error(path + ": palette index out of range");
+                r = palette[k];
+                g = palette[k + 1];
+                bl = palette[k + 2];
+            } else {
+                r = px[(size_t)x * ch];
+                g = px[(size_t)x * ch + 1];
+                bl = px[(size_t)x * ch + 2];
+            }
+            out[3 * x] = bl;  // cv::imread(IMREAD_COLOR) returns BGR and drops alpha
+            out[3 * x + 1] = g;
+            out[3 * x + 2] = r;
+        }
+    }
+}
+}  // namespace util
+
+namespace sources {
+namespace {
+constexpr int kLeftCam = 2, kRightCam = 3;  // kitti.cpp:11-12
+
+std::string addLeadingZeros(int number, size_t length) {  // kitti.cpp:18-21
+    const std::string s = std::to_string(number);
+    return std::string(length - std::min(length, s.length()), '0') + s;
+}
+
+struct Calibration {
+    int cameraId = -1;
+    float fx = 0, fy = 0, cx = 0, cy = 0, baseline = 0;
+};
+
+// One line of calib.txt, "P2: 12 floats" (kitti.cpp:32-85).  Like the reference, values are split at single spaces and
+// the line is accepted only when exactly 11 separators were seen (the 12th value is never needed).
+bool readLine(std::string line, Calibration& out) {
+    size_t pos = line.find(": ");
+    if (pos == std::string::npos) return false;
+    std::string token = line.substr(0, pos);
+    line.erase(0, pos + 2);
+    if (token.empty() || token[0] != 'P') return false;
+    Calibration local;
+    try {
+        local.cameraId = std::stoi(token.substr(1));
+        float fubx = 0;
+        int i = 0;
+        while ((pos = line.find(' ')) != std::string::npos) {
+            token = line.substr(0, pos);
+            line.erase(0, pos + 1);
+            switch (i) {
+                case 0: local.fx = std::stof(token); break;
+                case 5: local.fy = std::stof(token); break;
+                case 3: fubx = std::stof(token); break;
+                case 2: local.cx = std::stof(token); break;
+                case 6: local.cy = std::stof(token); break;
+            }
+            i++;
+        }
+        if (i != 11) return false;
+        local.baseline = -fubx / local.fx;
+    } catch (const std::exception&) {
+        return false;
+    }
+    out = local;
+    return true;
+}
+}  // namespace
+
+KITTIDataSource::KITTIDataSource(std::string basePath, int sequence, Size imageSize)
+    : DataSource(imageSize), path(util::resolvePath(basePath + "/sequences/" + addLeadingZeros(sequence, 2))) {
+    init();
+}
+
+KITTIDataSource::KITTIDataSource(std::string path_, Size imageSize) : DataSource(imageSize), path(util::resolvePath(path_)) { init(); }
+
+std::string KITTIDataSource::framePath(int cam, int frame) const {
+    return path + "/image_" + std::to_string(cam) + "/" + addLeadingZeros(frame, 6) + ".png";
+}
+
+void KITTIDataSource::init() {
+    const std::string calibPath = path + "/calib.txt";
+    std::ifstream in(calibPath);
+    if (!in.is_open()) throw std::runtime_error("Failed to open calibration file at " + calibPath + ": " + strerror(errno));
+    Calibration left, right;
+    bool haveLeft = false, haveRight = false;
+    std::string line;
+    while (std::getline(in, line)) {
+        Calibration c;
+        if (!readLine(line, c)) continue;
+        if (c.cameraId == kLeftCam) {
+            left = c;
+            haveLeft = true;
+        } else if (c.cameraId == kRightCam) {
+            right = c;
+            haveRight = true;
+        }
+    }
+    if (!haveLeft || !haveRight) throw std::runtime_error("Failed to read calibration file");
+    // the first image gives the native size (kitti.cpp:129-135)
+    int w = 0, h = 0;
+    util::readPngBgr(framePath(kLeftCam, 0), bufL, w, h);
+    if (imageSize.width == 0 || imageSize.height == 0) imageSize = Size(w, h);
+    if (imageSize.width != w || imageSize.height != h)
+        throw std::runtime_error("KITTIDataSource: resizing (cv::cuda::resize, kitti.cpp:166-169) is not supported; use the native image size");
+    const float scaleWidth = (float)imageSize.width / (float)w, scaleHeight = (float)imageSize.height / (float)h;
+    // reprojection matrix, kitti.cpp:141-148
+    CameraIntrinsics k;
+    k.Q[0 * 4 + 3] = -left.cx * scaleWidth;
+    k.Q[1 * 4 + 3] = -left.cy * scaleHeight;
+    k.Q[2 * 4 + 2] = 0;
+    k.Q[2 * 4 + 3] = left.fx * scaleWidth;
+    k.Q[3 * 4 + 2] = (float)(-1.0 / left.baseline);
+    k.Q[3 * 4 + 3] = (left.cx - right.cx) * scaleWidth / left.baseline;
+    intrinsics = k;
+}
+
+bool KITTIDataSource::isNextReady() {
+    struct stat st;
+    return stat(framePath(kLeftCam, currentFrame).c_str(), &st) == 0;
+}
+
+bool KITTIDataSource::isFinished() { return !isNextReady(); }
+
+std::shared_ptr<DataElement> KITTIDataSource::getNextInternal(void* stream) {
+    int wl = 0, hl = 0, wr = 0, hr = 0;
+    util::readPngBgr(framePath(kLeftCam, currentFrame), bufL, wl, hl);
+    util::readPngBgr(framePath(kRightCam, currentFrame), bufR, wr, hr);
+    if (wl != imageSize.width || hl != imageSize.height || wr != wl || hr != hl)
+        throw std::runtime_error("KITTIDataSource: frame " + std::to_string(currentFrame) + " has a different size");
+    ++currentFrame;
+    image_t l(imageSize.height, imageSize.width, IMG_8UC3), r(imageSize.height, imageSize.width, IMG_8UC3);
+    l.upload(bufL.data(), (size_t)imageSize.width * 3, stream);
+    r.upload(bufR.data(), (size_t)imageSize.width * 3, stream);
+    syncStream(stream);  // bufL / bufR are reused by the next frame
+    return std::make_shared<StereoDataElement>(l, r);
+}
+}  // namespace sources
+}  // namespace cart
