@@ -35,6 +35,12 @@ sys.path.insert(0, ROOT)
 W, H, D, MIN_DISP = 1242, 375, 128, 4
 METRIC = "stereo frames/s (1242x375, 128 disp) disparity->planeseg"
 UNIT = "frames/s"
+# BASELINE.json configs: [1] is the headline (default); [2] and [3] are recorded with --workload zed / 4k
+WORKLOADS = {
+    "kitti": dict(W=1242, H=375, D=128, paths=4, block=12, frames=1000, batch=64, pipeline=1, provider=1),
+    "zed": dict(W=1280, H=720, D=256, paths=4, block=16, frames=200, batch=16, pipeline=1, provider=0),
+    "4k": dict(W=3840, H=2160, D=256, paths=8, block=48, frames=20, batch=4, pipeline=0, provider=1),
+}
 
 
 def load_peaks():
@@ -222,20 +228,31 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cartb200", choices=["cartb200", "reference"])
-    ap.add_argument("--frames", type=int, default=1000, help="frames per sequence (BASELINE.json configs[1]: 1000)")
-    ap.add_argument("--batch", type=int, default=64, help="frames per batched launch (SGM stages); superpixel slots = sequence chunks")
-    ap.add_argument("--pipeline", type=int, default=1, help="1 = superpixel pipeline (headline), 0 = naive")
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=None, help="frames per sequence (BASELINE.json configs[1]: 1000)")
+    ap.add_argument("--batch", type=int, default=None, help="frames per batched launch (SGM stages); superpixel slots = sequence chunks")
+    ap.add_argument("--pipeline", type=int, default=None, help="1 = superpixel pipeline (headline), 0 = naive")
     ap.add_argument("--cpu-sample", type=int, default=6)
     args = ap.parse_args()
+    global W, H, D, METRIC
+    wl = WORKLOADS[args.workload]
+    W, H, D = wl["W"], wl["H"], wl["D"]
+    if args.workload != "kitti":
+        METRIC = f"stereo frames/s ({W}x{H}, {D} disp, {wl['paths']} paths) disparity->planeseg"
+    args.frames = args.frames or wl["frames"]
+    args.batch = args.batch or wl["batch"]
+    args.pipeline = wl["pipeline"] if args.pipeline is None else args.pipeline
+    n_paths, sp_block, provider = wl["paths"], wl["block"], wl["provider"]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfg_workload = {
-        "workload": f"KITTI-shaped synthetic {args.frames}-frame stereo sequence per GPU, {W}x{H}, {D} disparities, "
-                    f"min_disparity {MIN_DISP}, 4 paths (MODE_HH4), smoothing r=2 it=1, "
-                    + ("superpixels 24/8 iterations block 12 reset 64 + superpixel planeseg (kitti-planeseg.json minus optflow/depth/vis/temporal), histogram_peak provider"
-                       if args.pipeline == 1 else "naive planeseg (kitti-naive-segmentation.json), histogram_peak provider"),
+        "workload": f"{args.workload}-shaped synthetic {args.frames}-frame stereo sequence per GPU, {W}x{H}, {D} disparities, "
+                    f"min_disparity {MIN_DISP}, {n_paths} paths ({'MODE_HH4' if n_paths == 4 else 'MODE_HH'}), smoothing r=2 it=1, "
+                    + (f"superpixels 24/8 iterations block {sp_block} reset 64 + superpixel planeseg (kitti-planeseg.json minus optflow/depth/vis/temporal), "
+                       if args.pipeline == 1 else "naive planeseg (kitti-naive-segmentation.json), ")
+                    + ("histogram_peak provider" if provider == 1 else "static ranges h [1,30) v [-3,1)"),
         "frames_per_gpu": args.frames, "batch": args.batch, "pipeline": "superpixel" if args.pipeline == 1 else "naive",
         "l2": "inputs and intermediates per step (>= 2.8 GB images, 3.8 GB cost volumes per batch) exceed the 126 MB L2",
     }
@@ -282,11 +299,11 @@ def main():
     planes_host = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
     torch.cuda.synchronize()
 
-    cfg = cb.Config(W, H, max_batch=args.batch, num_disparities=D, min_disparity=MIN_DISP, smoothing_radius=2,
-                    smoothing_iterations=1, enable_superpixels=args.pipeline == 1, sp_block_size=12)
+    cfg = cb.Config(W, H, max_batch=args.batch, num_disparities=D, min_disparity=MIN_DISP, paths=n_paths, smoothing_radius=2,
+                    smoothing_iterations=1, enable_superpixels=args.pipeline == 1, sp_block_size=sp_block)
     ctx = cb.Context(cfg)
-    opts = cb.SequenceOptions(pipeline=args.pipeline, provider=1, sp_initial_iterations=24, sp_iterations=8,
-                              sp_reset_iterations=64)
+    opts = cb.SequenceOptions(pipeline=args.pipeline, provider=provider, static_params=(1, 30, -3, 1), sp_initial_iterations=24,
+                              sp_iterations=8, sp_reset_iterations=64)
     gather_buf = None
     if world > 1 and rank == 0:
         gather_buf = [torch.empty_like(planes_dev) for _ in range(world)]
@@ -353,20 +370,20 @@ def main():
             ctx.sgm_aggregate(nb)
         a1.record()
         torch.cuda.synchronize()
-        per_kernel_ms = a0.elapsed_time(a1) / reps / 4  # 4 path kernels per call
+        per_kernel_ms = a0.elapsed_time(a1) / reps / n_paths  # time per path
         alg_bytes = nb * (2 * 4 * W * H + W * H * D)   # read both census images, write one u8 volume
         achieved = alg_bytes / (per_kernel_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "aggregate_horizontal_kernel / aggregate_vertical_kernel (mean over the 4 MODE_HH4 "
+        roof = {"bound": "hbm", "kernel": f"aggregate_horizontal_kernel / aggregate_vertical_kernel (mean over the {n_paths} "
                                           f"paths, {nb}-frame batch; opposite directions share a launch, time is per path)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": ncu_traffic_per_launch() if nb == 64 else None, "peak_source": peak_src,
+                "traffic": ncu_traffic_per_launch() if (nb == 64 and args.workload == "kitti") else None, "peak_source": peak_src,
                 "launch_ms": per_kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "compute-limited: every path recomputes the Hamming costs, the POPC pipe (15 lanes/clk/SM "
                         "measured) caps four paths at 69 % of the HBM peak (DESIGN.md section 4)"}
 
     cpu = None
     ref_gpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.workload == "kitti":  # the other workloads are recorded without CPU arms
         v, threads, sample = cpu_arm(args.cpu_sample, L, R)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
         ref_gpu = reference_gpu_kernels()
