@@ -675,7 +675,12 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
     if (!q->copyStream) {
         CB_CHECK_CUDA(c, cudaStreamCreateWithFlags(&q->copyStream, cudaStreamNonBlocking));
         for (auto& e : q->evIn) CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        CB_CHECK_CUDA(c, cudaStreamCreateWithFlags(&q->spStream, cudaStreamNonBlocking));
+        {   // the latency-bound superpixel kernels get the higher priority: their blocks take free SM slots first,
+            // the pipe-bound SGM kernels of the next batch fill the rest
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            CB_CHECK_CUDA(c, cudaStreamCreateWithPriority(&q->spStream, cudaStreamNonBlocking, hi));
+        }
         CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&q->evStart, cudaEventDisableTiming));
         CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&q->evSpDone, cudaEventDisableTiming));
     }
