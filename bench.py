@@ -287,6 +287,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL's own log lines (its version banner at NCCL_DEBUG >= VERSION) go to stderr: stdout carries the JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hbm_peak, peak_src = load_peaks()
 
