@@ -292,3 +292,79 @@ def test_depth_matches_oracle(gpu):
         fin = np.isfinite(o)
         assert np.array_equal(np.isfinite(xyz[f]), fin)
         assert np.allclose(xyz[f][fin], o[fin], rtol=1e-6, atol=0)
+
+
+def _check_sgm_full_size(gpu, W, H, D, paths, rows_sampled, seed):
+    """BASELINE.json full sizes where the scalar oracle is too slow for whole volumes: every stage is still checked
+    exactly, through properties that do not need the oracle's full run -
+      census       = oracle census of the oracle gray image (cheap, whole image);
+      path volumes = the recurrence D4 re-evaluated in numpy on sampled pixels FROM THE GPU'S OWN predecessor
+                     vectors and the census words (self-consistency of every path at full size);
+      raw WTA      = oracle WTA (D5, D6) on sampled full rows of the GPU's volumes (rows are independent);
+      disparity    = oracle medians + L/R check + range correction (D7-D9) on the GPU's raw WTA images (whole image)."""
+    md, P1, P2 = 4, 10, 120
+    seq = SyntheticSequence(W, H, D, min_disp=md, n_frames=2)
+    l, r, _ = seq.frame(1)
+    cfg = cb.Config(W, H, max_batch=1, num_disparities=D, min_disparity=md, paths=paths, enable_superpixels=False)
+    rng = np.random.default_rng(seed)
+    with cb.Context(cfg) as ctx:
+        ctx.sgm_gray_census(dev(l[None]), dev(r[None]))
+        ctx.sgm_aggregate(1)
+        disp = host(ctx.sgm_wta_post(1))[0]
+        gl = host(ctx.sgm_intermediate(2, 1))[0]
+        cl, cr = host(ctx.sgm_intermediate(0, 1))[0], host(ctx.sgm_intermediate(1, 1))[0]
+        assert np.array_equal(gl, po.gray(l))
+        assert np.array_equal(cl, po.census(po.gray(l))) and np.array_equal(cr, po.census(po.gray(r)))
+        wl, wr = host(ctx.sgm_intermediate(3, 1))[0], host(ctx.sgm_intermediate(4, 1))[0]
+        ys = np.sort(rng.choice(H, rows_sampled, replace=False))
+        row_vols = []
+        dirs = po.sgm_dirs(paths)
+        d = np.arange(D)
+        for p in range(paths):
+            vol = ctx.sgm_intermediate(10 + p, 1)[0]  # [H, W, D] on the device
+            assert int(vol.max()) <= 31 + P2
+            row_vols.append(vol[torch.from_numpy(ys).to(vol.device)].cpu().numpy())
+            dx, dy = int(dirs[p][0]), int(dirs[p][1])
+            # recurrence on sampled pixels (vectorised over the samples and over d)
+            n = 4000
+            sx, sy = rng.integers(0, W, n), rng.integers(0, H, n)
+            px, py = sx - dx, sy - dy
+            inside = (px >= 0) & (px < W) & (py >= 0) & (py < H)
+            cur = vol[torch.from_numpy(sy).to(vol.device), torch.from_numpy(sx).to(vol.device)].cpu().numpy().astype(np.int64)
+            prev = vol[torch.from_numpy(np.clip(py, 0, H - 1)).to(vol.device),
+                       torch.from_numpy(np.clip(px, 0, W - 1)).to(vol.device)].cpu().numpy().astype(np.int64)
+            prev[~inside] = 0  # a path starts from the all-zero state where it enters the image
+            xr = sx[:, None] - d[None, :] - md
+            rword = np.where((xr >= 0) & (xr < W), cr[sy[:, None], np.clip(xr, 0, W - 1)], 0).astype(np.uint32)
+            x = (cl[sy, sx][:, None] ^ rword).astype(np.uint32)
+            cost = np.zeros(x.shape, np.int64)
+            for b in range(32):
+                cost += (x >> np.uint32(b)) & np.uint32(1)
+            m = prev.min(1, keepdims=True)
+            big = 1 << 20
+            lo = np.concatenate([np.full((n, 1), big), prev[:, :-1] + P1], 1)
+            hi = np.concatenate([prev[:, 1:] + P1, np.full((n, 1), big)], 1)
+            exp = cost + np.minimum(np.minimum(prev, m + P2), np.minimum(lo, hi)) - m
+            bad = np.argwhere(exp != cur)
+            assert bad.size == 0, (p, bad[:3], sx[bad[:3, 0]], sy[bad[:3, 0]])
+            del vol
+        for i, y in enumerate(ys):
+            o_l, o_r = po.sgm_wta([rv[i][None] for rv in row_vols])
+            assert np.array_equal(wl[y], o_l[0]), ("WTA left row", y)
+            assert np.array_equal(wr[y], o_r[0]), ("WTA right row", y)
+        o_disp = po.lr_check_range(po.median3(wl), po.median3(wr), gl, md)
+        assert np.array_equal(disp, o_disp)
+        # determinism: a second run gives identical bits
+        ctx.sgm_gray_census(dev(l[None]), dev(r[None]))
+        ctx.sgm_aggregate(1)
+        assert np.array_equal(host(ctx.sgm_wta_post(1))[0], disp)
+
+
+def test_full_size_zed_properties(gpu):
+    """BASELINE.json configs[2]: 1280x720, 256 disparities (4 paths)."""
+    _check_sgm_full_size(gpu, 1280, 720, 256, 4, rows_sampled=6, seed=11)
+
+
+def test_full_size_4k_8path_properties(gpu):
+    """BASELINE.json configs[3]: 3840x2160, 256 disparities, 8-path aggregation."""
+    _check_sgm_full_size(gpu, 3840, 2160, 256, 8, rows_sampled=4, seed=12)
