@@ -1,0 +1,75 @@
+"""Label agreement between the CUDA superpixel relaxation and the scalar oracle over one full warm-started chain
+(KITTI size, frames 1..N with 24 iterations on frame 1 and 8 afterwards, as SuperPixelModule schedules them).
+Both sides get the same inputs (the CUDA path's disparity derivative, which is bit-exact against the oracle).
+Run on the GPU box:  python tools/sp_chain_agreement.py [--frames 64]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import pyoracle as po  # noqa: E402
+
+import cart_slam_b200 as cb  # noqa: E402
+from cart_slam_b200.synth import SyntheticSequence  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=63)
+    args = ap.parse_args()
+    W, H, D = 1242, 375, 128
+    seq = SyntheticSequence(W, H, D, min_disp=4, n_frames=args.frames + 1, tint=True)
+    cfg = cb.Config(W, H, max_batch=1, num_disparities=D, smoothing_radius=2, smoothing_iterations=1, sp_block_size=12)
+    o_lab, nlab = po.block_init(W, H, 12, 12)
+    # the reference's own kernels (oracle/_ref/libref.so), run twice: their stored feature costs race, so
+    # even the reference does not reproduce itself over a warm-started chain
+    import ctypes as C
+    ref = None
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libref.so")
+    if os.path.exists(ref_path):
+        ref = C.CDLL(ref_path)
+        ref.ref_relax.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_double] * 6 + [C.c_void_p]
+    r_lab_a, r_lab_b = o_lab.copy(), o_lab.copy()
+    ms = C.c_float()
+    ref_self, ref_vs_oracle, ours_vs_ref = [], [], []
+    agree = []
+    t0 = time.time()
+    with cb.Context(cfg) as ctx:
+        ctx.superpixels_reset(1)
+        for i in range(1, args.frames + 1):
+            l, r, _ = seq.frame(i)
+            dl, dr = torch.from_numpy(l).cuda()[None], torch.from_numpy(r).cuda()[None]
+            disp = ctx.disparity(dl, dr)
+            deriv, _ = ctx.derivative(disp)
+            its = 24 if i == 1 else 8
+            g_lab = ctx.superpixels_relax(dl, deriv, its)[0].cpu().numpy()
+            o_lab, _, _ = po.sp_relax(o_lab, nlab, po.ycrcb(l), deriv[0].cpu().numpy(), its)
+            agree.append(float((g_lab == o_lab).mean()))
+            if ref is not None:
+                ycc = po.ycrcb(l)
+                dv = np.ascontiguousarray(deriv[0].cpu().numpy())
+                for lab in (r_lab_a, r_lab_b):
+                    ref.ref_relax(lab.ctypes.data, W, H, nlab, ycc.ctypes.data, dv.ctypes.data, its, 0.5, 0.5 / np.sqrt(2), 0.1, 0.0,
+                                  1.0, 1.5, C.byref(ms))
+                ref_self.append(float((r_lab_a == r_lab_b).mean()))
+                ref_vs_oracle.append(float((r_lab_a == o_lab).mean()))
+                ours_vs_ref.append(float((g_lab == r_lab_a).mean()))
+            print(f"frame {i:3d}: ours/oracle {agree[-1]:.6f}" + (f"  reference/reference {ref_self[-1]:.6f}  reference/oracle "
+                  f"{ref_vs_oracle[-1]:.6f}  ours/reference {ours_vs_ref[-1]:.6f}" if ref is not None else ""), flush=True)
+    out = {"frames": args.frames, "min": min(agree), "mean": float(np.mean(agree)), "last": agree[-1], "per_frame": agree, "reference_vs_itself": ref_self, "reference_vs_oracle": ref_vs_oracle, "ours_vs_reference": ours_vs_ref,
+           "seconds": time.time() - t0,
+           "what": "fraction of pixels with identical superpixel labels, CUDA path vs scalar oracle, one warm-started chain at 1242x375 (block 12)"}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "sp_chain_agreement.json"), "w"), indent=1)
+    print(json.dumps({k: v for k, v in out.items() if not isinstance(v, list)}))
+
+
+if __name__ == "__main__":
+    main()
