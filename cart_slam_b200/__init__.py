@@ -44,7 +44,7 @@ class _CConfig(C.Structure):
         ("smoothing_iterations", C.c_int), ("enable_superpixels", C.c_int), ("sp_block_size", C.c_int),
         ("sp_direct_clique_cost", C.c_double), ("sp_diagonal_clique_cost", C.c_double),
         ("sp_compactness_weight", C.c_double), ("sp_progressive_compactness_cost", C.c_double),
-        ("sp_image_weight", C.c_double), ("sp_disparity_weight", C.c_double),
+        ("sp_image_weight", C.c_double), ("sp_disparity_weight", C.c_double), ("sp_exact", C.c_int),
     ]
 
 
@@ -145,6 +145,7 @@ class Config:
     sp_progressive_compactness_cost: float = 0.0
     sp_image_weight: float = 1.5
     sp_disparity_weight: float = 1.0
+    sp_exact: bool = False  # True: label costs in the reference's operation order, bit-identical to the oracle
 
     def to_c(self) -> _CConfig:
         c = _CConfig()

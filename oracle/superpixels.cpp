@@ -37,11 +37,51 @@ struct Stat {  // LabelStatisticsGauss, gaussian.cuh:18-28
     double sum = 0, sq = 0, cost = 0;
 };
 
+// The reference calls CUDA's device log() (gaussian.cu:41), whose last bits no CPU library reproduces.  The oracle
+// therefore fixes a fully specified logarithm: the main path of fdlibm's e_log with IEEE +, -, *, / in a fixed order
+// and no fused multiply-adds (this file is built with -ffp-contract=off).  Any implementation that keeps the order
+// gets the same bits, which allows a bit-exact parity test of the label decisions.  Domain: x >= 2 pi / 12.
+inline double detLog(double x) {
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    uint64_t bits;
+    std::memcpy(&bits, &x, 8);
+    int32_t hx = (int32_t)(bits >> 32);
+    const uint32_t lx = (uint32_t)bits;
+    int32_t k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    int32_t i = (hx + 0x95f64) & 0x100000;
+    const uint64_t mbits = ((uint64_t)(uint32_t)(hx | (i ^ 0x3ff00000)) << 32) | lx;
+    double m;
+    std::memcpy(&m, &mbits, 8);
+    k += i >> 20;
+    const double f = m - 1.0;
+    const double s = f / (2.0 + f);
+    const double dk = (double)k;
+    const double z = s * s;
+    i = hx - 0x6147a;
+    const double w = z * z;
+    const int32_t j = 0x6b851 - hx;
+    const double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    const double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    i |= j;
+    const double R = t2 + t1;
+    if (i > 0) {
+        const double hfsq = (0.5 * f) * f;
+        if (k == 0) return f - (hfsq - s * (hfsq + R));
+        return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+    }
+    if (k == 0) return f - s * (f - R);
+    return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+}
+
 inline void gaussCost(Stat& s) {  // deviceUpdateLabelFeatureCost, gaussian.cu:30-43
     const double n = (double)s.n;
     double variance = (s.sq / n) - ((s.sum / n) * (s.sum / n));
     variance = std::fmax(variance, kMinVariance);
-    s.cost = (n / 2 * std::log(2 * M_PI * variance)) + (n / 2);
+    s.cost = (n / 2 * detLog(2 * M_PI * variance)) + (n / 2);
 }
 inline void compactCost(Stat& s) {  // updateCompactnessCost, compactness.cu:28-35
     if (s.n == 0) {

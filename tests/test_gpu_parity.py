@@ -162,6 +162,31 @@ def test_superpixel_relax_agreement(gpu, case):
             ctx.superpixels_set_labels(1, dev(lab_o))
 
 
+@pytest.mark.parametrize("case", SP_CASES, ids=lambda c: f"{c['W']}x{c['H']}b{c['block']}")
+def test_superpixel_exact_mode_is_bit_identical_over_a_chain(gpu, case):
+    """sp_exact = 1: label costs in the reference's operation order with the fully specified logarithm - the labels
+    equal the oracle's bit for bit, frame after frame of a warm-started chain (no re-synchronisation of the state)."""
+    W, H, block, its, kw = case["W"], case["H"], case["block"], case["its"], case["kw"]
+    n_frames = 12
+    seq = SyntheticSequence(W, H, 64, n_frames=n_frames + 1, tint=True)
+    cfg = cb.Config(W, H, max_batch=1, num_disparities=64, smoothing_radius=2, smoothing_iterations=1,
+                    sp_block_size=block, sp_compactness_weight=kw.get("w_compact", 0.1),
+                    sp_progressive_compactness_cost=kw.get("progressive", 0.0),
+                    sp_disparity_weight=kw.get("w_disp", 1.0), sp_exact=True)
+    with cb.Context(cfg) as ctx:
+        lab_o, nlab = po.block_init(W, H, block, block)
+        ctx.superpixels_reset(1)
+        for fid in range(1, n_frames + 1):
+            l, r, _ = seq.frame(fid)
+            disp = ctx.disparity(dev(l[None]), dev(r[None]))
+            deriv, _ = ctx.derivative(disp)
+            use_d = kw.get("w_disp", 1.0) > 0
+            got = host(ctx.superpixels_relax(dev(l[None]), deriv if use_d else None, its))[0]
+            lab_o, _, mv = po.sp_relax(lab_o, nlab, po.ycrcb(l), host(deriv)[0] if use_d else None, its, **kw)
+            assert np.array_equal(got, lab_o), (fid, float((got == lab_o).mean()))
+            assert mv.sum() > 0
+
+
 def test_sp_planeseg_exact(gpu):
     W, H = 200, 120
     rng = np.random.default_rng(4)
