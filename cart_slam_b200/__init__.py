@@ -145,7 +145,7 @@ class Config:
     sp_progressive_compactness_cost: float = 0.0
     sp_image_weight: float = 1.5
     sp_disparity_weight: float = 1.0
-    sp_exact: bool = False  # True: label costs in the reference's operation order, bit-identical to the oracle
+    sp_exact: bool = True  # label costs in the reference's operation order: labels bit-identical to the oracle; False = faster cost differences
 
     def to_c(self) -> _CConfig:
         c = _CConfig()

@@ -139,6 +139,7 @@ void cartb200_default_config(cartb200_config* cfg, int width, int height) {
     cfg->sp_progressive_compactness_cost = 0.0;
     cfg->sp_image_weight = 1.5;              // :132
     cfg->sp_disparity_weight = 1.0;          // :133
+    cfg->sp_exact = 1;
 }
 
 void cartb200_default_sequence_opts(cartb200_sequence_opts* o) {
