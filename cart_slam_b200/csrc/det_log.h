@@ -39,7 +39,14 @@ DETLOG_HD double det_log(double x) {
 #endif
     k += i >> 20;
     const double f = m - 1.0;
+#if defined(__CUDA_ARCH__)
+    // correctly rounded quotient without the full division sequence: y = RN(1 / t), q = RN(f y), r = f - t q (exact),
+    // RN(q + r y) = RN(f / t) (Markstein) - the same bits as the IEEE division of the host build
+    const double t = 2.0 + f, y = __drcp_rn(t), q0 = f * y;
+    const double s = fma(fma(-t, q0, f), y, q0);
+#else
     const double s = f / (2.0 + f);
+#endif
     const double dk = (double)k;
     const double z = s * s;
     i = hx - 0x6147a;
