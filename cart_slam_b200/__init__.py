@@ -82,6 +82,7 @@ def _load():
     lib.cartb200_sgm_wta_post.argtypes = [vp, i, vp, sz, sz, vp]
     lib.cartb200_interpolate.argtypes = [vp, i, vp, sz, sz, i, i, i, i, vp]
     lib.cartb200_sgm_intermediate.argtypes = [vp, i, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
+    lib.cartb200_last_create_error.restype = C.c_char_p
     lib.cartb200_derivative.argtypes = [vp, i, vp, sz, sz, vp, sz, sz, vp, vp]
     lib.cartb200_depth.argtypes = [vp, i, vp, sz, sz, vp, vp, sz, sz, vp]
     lib.cartb200_naive_derivative.argtypes = [vp, i, vp, sz, sz, vp, sz, sz, vp, vp]
@@ -104,7 +105,7 @@ def _load():
 _lib = _load()
 
 EXPORTED_SYMBOLS = [
-    "cartb200_default_config", "cartb200_create", "cartb200_destroy", "cartb200_last_error", "cartb200_version",
+    "cartb200_default_config", "cartb200_create", "cartb200_last_create_error", "cartb200_destroy", "cartb200_last_error", "cartb200_version",
     "cartb200_launch_count", "cartb200_scratch_bytes", "cartb200_disparity", "cartb200_sgm_gray_census",
     "cartb200_sgm_aggregate", "cartb200_sgm_aggregate_path", "cartb200_sgm_wta_post", "cartb200_interpolate", "cartb200_sgm_intermediate",
     "cartb200_derivative", "cartb200_depth", "cartb200_naive_derivative", "cartb200_classify", "cartb200_superpixels_reset",
@@ -228,7 +229,7 @@ class Context:
         c = cfg.to_c()
         rc = _lib.cartb200_create(C.byref(c), C.byref(self._h))
         if rc != OK:
-            raise CartB200Error(rc, "cartb200_create failed (see stderr)")
+            raise CartB200Error(rc, _lib.cartb200_last_create_error().decode() or "cartb200_create failed")
         self.W, self.H, self.D, self.B = cfg.width, cfg.height, cfg.num_disparities, cfg.max_batch
         self.max_label = -(-cfg.width // cfg.sp_block_size) * -(-cfg.height // cfg.sp_block_size)
 

@@ -113,9 +113,14 @@ int checkBatch(cartb200_ctx* c, int n) {
 
 }  // namespace
 
+namespace {
+thread_local std::string g_createError;
+}
+
 extern "C" {
 
 const char* cartb200_version(void) { return "cartb200 0.1 (sm_100a)"; }
+const char* cartb200_last_create_error(void) { return g_createError.c_str(); }
 
 void cartb200_default_config(cartb200_config* cfg, int width, int height) {
     std::memset(cfg, 0, sizeof(*cfg));
@@ -163,6 +168,7 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
     auto fail = [&](int rc) {
         // keep the message reachable: the caller cannot read it from a destroyed context, so print it
         fprintf(stderr, "cartb200_create: %s\n", c->err.c_str());
+        g_createError = c->err;
         cartb200_destroy(c);
         return rc;
     };

@@ -74,6 +74,8 @@ typedef struct cartb200_config {
 void cartb200_default_config(cartb200_config* cfg, int width, int height);
 
 int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out);
+/* Description of the last failed cartb200_create on the calling thread (a failed create leaves no context to ask). */
+const char* cartb200_last_create_error(void);
 void cartb200_destroy(cartb200_ctx* ctx);
 const char* cartb200_last_error(const cartb200_ctx* ctx);
 const char* cartb200_version(void);

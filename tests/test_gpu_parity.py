@@ -400,3 +400,37 @@ def test_full_size_zed_properties(gpu):
 def test_full_size_4k_8path_properties(gpu):
     """BASELINE.json configs[3]: 3840x2160, 256 disparities, 8-path aggregation."""
     _check_sgm_full_size(gpu, 3840, 2160, 256, 8, rows_sampled=4, seed=12)
+
+
+def test_c_abi_error_paths(gpu):
+    """Error behaviour at the boundary: return codes + messages, nothing throws inside the library, nothing exits
+    (the reference logs and exit()s on CUDA errors and throws std::runtime_error on type guards)."""
+    W, H = 96, 48
+    with pytest.raises(cb.CartB200Error, match="num_disparities must be 64, 128 or 256"):
+        cb.Context(cb.Config(W, H, num_disparities=100))
+    with pytest.raises(cb.CartB200Error, match="paths must be 4"):
+        cb.Context(cb.Config(W, H, num_disparities=64, paths=5))
+    with pytest.raises(cb.CartB200Error, match="31 \\+ p2 <= 255"):
+        cb.Context(cb.Config(W, H, num_disparities=64, p2=240))
+    with pytest.raises(cb.CartB200Error, match="below 16384"):
+        cb.Context(cb.Config(2048, 1024, num_disparities=64, enable_sgm=False, sp_block_size=8))
+    cfg = cb.Config(W, H, max_batch=2, num_disparities=64, enable_superpixels=False)
+    with cb.Context(cfg) as ctx:
+        L = torch.zeros((3, H, W, 3), dtype=torch.uint8, device="cuda")
+        with pytest.raises(cb.CartB200Error, match="batch size 3 outside 1..2"):
+            ctx.disparity(L, L)
+        with pytest.raises(cb.CartB200Error, match="path index out of range"):
+            ctx.sgm_aggregate_path(1, 4)
+        d = torch.zeros((1, H, W), dtype=torch.int16, device="cuda")
+        with pytest.raises(cb.CartB200Error, match="without superpixels"):
+            ctx.superpixels_reset(1)
+        with pytest.raises(cb.CartB200Error, match="superpixel pipeline needs enable_superpixels"):
+            ctx.run_sequence_device(cb.SequenceOptions(pipeline=1), L[:2], L[:2])
+        # the context stays usable after an error
+        out = ctx.disparity(L[:2], L[:2])
+        assert out.shape == (2, H, W)
+    sgm_off = cb.Config(W, H, max_batch=1, enable_sgm=False, enable_superpixels=False)
+    with cb.Context(sgm_off) as ctx:
+        L = torch.zeros((1, H, W, 3), dtype=torch.uint8, device="cuda")
+        with pytest.raises(cb.CartB200Error, match="enable_sgm = 0"):
+            ctx.disparity(L, L)
