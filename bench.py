@@ -124,9 +124,14 @@ def ncu_traffic_per_launch():
     """dram__bytes_read + dram__bytes_write of one aggregation-path launch (64-frame batch) from the committed
     `ncu --set full` summary (profiles/), or None."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01b_ncu_sgm_batch64.json")))
+        launches = []
+        for name in ("r01h_ncu_aggregate_horizontal_batch64.json", "r01b_ncu_sgm_batch64.json"):  # newest capture first
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(path):
+                launches = json.load(open(path))["launches"]
+                break
         tot = []
-        for l in d["launches"]:
+        for l in launches:
             if "aggregate_" not in l["kernel"]:
                 continue
             b = 0.0
