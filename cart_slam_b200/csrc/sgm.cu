@@ -5,7 +5,7 @@
 // Layout in HBM (per context, sized for max_batch frames):
 //   gray   u8  [B][H][grayPitch]          census u32 [B][H][censusPitch/4]
 //   volume u8  [P][B][H][W][D]   (D contiguous: one pixel's disparity vector is one or two 128-B lines)
-//   wta    u16 [B][H][dispPitch/2] x {left raw, right raw}
+//   wta    left raw u16 [B][H][dispPitch/2]; right raw as u32 keys (cost, cost high byte, disparity) [B][H][rkPitch]
 // Arithmetic: path costs are <= 31 + P2 (u8 in memory); inside the kernels two disparities share a
 // register as u16x2 and the recurrence runs on the DPX/video integer instructions of sm_90+/sm_100
 // (VIADDMNMX.U16x2, VIMNMX.U16x2, VIMNMX3) - no tensor cores: nothing here is a dense contraction.
@@ -83,10 +83,12 @@ int launch_gray_census(cartb200_ctx* c, int n, ImgBatch<const uint8_t> left, Img
 // on packed halves (VIMNMX3.U16x2), a min-reduction over the group by warp shuffles and one 16-byte
 // store per lane (a group writes the pixel's whole D-vector: full 128-B lines).
 //   * horizontal paths: one group per image row; the right-census words a lane needs slide by one per
-//     step, so a 32-word register window is refilled with four 16-byte loads every 16 steps;
+//     step, so a (16 + 8)-word register window is refilled with two 16-byte loads every 8 steps (the next
+//     refill is prefetched);
 //   * vertical paths: one group per FOUR adjacent columns (register blocking in x: 20 census words serve
 //     64 cells), five 16-byte loads per row;
-//   * diagonal paths (MODE_HH only): generic kernel, one group per path line.
+//   * diagonal paths (MODE_HH only): the vertical sweep over skewed columns (aggregate_diagonal_kernel); the
+//     first, generic one-group-per-path-line kernel is kept for cross-checks.
 struct PathArgs {
     const uint32_t* cenL;   // row layout: [margin zeros][W census words][zeros]; points at element 0 of row 0
     const uint32_t* cenR;   // right census stored shifted by min_disparity (word for (x, d) at index x - d)
