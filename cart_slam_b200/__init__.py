@@ -56,6 +56,11 @@ class _CSeqOpts(C.Structure):
     ]
 
 
+class _CTemporalRef(C.Structure):  # cartb200_temporal_ref
+    _fields_ = [("planes_unsmoothed", C.c_void_p), ("planes_pitch", C.c_size_t), ("optflow", C.c_void_p),
+                ("optflow_pitch", C.c_size_t)]
+
+
 def _load():
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
@@ -93,6 +98,10 @@ def _load():
     lib.cartb200_superpixels_border_map.argtypes = [vp, vp, sz, vp, sz, vp]
     lib.cartb200_sp_planeseg.argtypes = [vp, i, vp, sz, sz, vp, sz, sz, i, vp, vp, vp, sz, sz, vp]
     lib.cartb200_histogram_peak_update.argtypes = [vp, vp]
+    lib.cartb200_classify_temporal.argtypes = [vp, vp, sz, i, i, vp, i, vp, vp, vp, sz, vp]
+    lib.cartb200_sp_planeseg_temporal.argtypes = [vp, vp, sz, vp, sz, i, vp, i, vp, vp, vp, sz, vp]
+    lib.cartb200_label_statistics.argtypes = [vp, vp, sz, vp, sz, i, vp, vp, vp]
+    lib.cartb200_region_inliers.argtypes = [vp, vp, sz, vp, sz, i, vp, i, C.c_double, vp, vp]
     lib.cartb200_run_sequence_host.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp, vp]
     lib.cartb200_run_sequence_device.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp, vp, vp]
     lib.cartb200_debug_ref_tile_i32.restype = C.c_int32
@@ -386,6 +395,68 @@ class Context:
                                               unsm.data_ptr(), planes.data_ptr(), self.W, self.W * self.H, self._stream()))
         torch.cuda.current_stream().synchronize()
         return unsm, planes
+
+    # -- temporal smoothing vote --------------------------------------------------
+    def _temporal_refs(self, prev_planes, prev_flow):
+        torch = self.torch
+        assert len(prev_planes) == len(prev_flow)
+        arr = (_CTemporalRef * max(1, len(prev_planes)))()
+        for k, (pl, fl) in enumerate(zip(prev_planes, prev_flow)):
+            assert pl.is_cuda and pl.dtype == torch.uint8 and pl.shape == (self.H, self.W) and pl.stride(1) == 1
+            assert fl.is_cuda and fl.dtype == torch.int16 and fl.shape == (self.H, self.W, 2) and fl.stride(2) == 1 and fl.stride(1) == 2
+            arr[k] = _CTemporalRef(pl.data_ptr(), pl.stride(0), fl.data_ptr(), fl.stride(0) * 2)
+        return arr
+
+    def classify_temporal(self, deriv, params, prev_planes, prev_flow):
+        """One frame. deriv: [H,W] or [H,W,2] int16; prev_planes[k]: planes_unsmoothed of frame id-(k+1) [H,W] u8;
+        prev_flow[k]: optflow of frame id-k [H,W,2] int16 (S10.5).  Returns (planes_unsmoothed, planes)."""
+        torch = self.torch
+        channels = 1 if deriv.dim() == 2 else deriv.shape[2]
+        _, p, pitch, _ = self._img(deriv[None], torch.int16)
+        pr = self._params(params, 1)
+        refs = self._temporal_refs(prev_planes, prev_flow)
+        unsm = torch.empty((self.H, self.W), dtype=torch.uint8, device=deriv.device)
+        sm = torch.empty_like(unsm)
+        self._check(_lib.cartb200_classify_temporal(self._h, p, pitch, channels, 0, pr.ctypes.data, len(prev_planes), refs,
+                                                    unsm.data_ptr(), sm.data_ptr(), self.W, self._stream()))
+        return unsm, sm
+
+    def sp_planeseg_temporal(self, deriv, labels, params, prev_planes, prev_flow, max_label=None):
+        torch = self.torch
+        _, dp, dpitch, _ = self._img(deriv[None], torch.int16, 2)
+        _, lp, lpitch, _ = self._img(labels[None], torch.uint16)
+        pr = self._params(params, 1)
+        refs = self._temporal_refs(prev_planes, prev_flow)
+        unsm = torch.empty((self.H, self.W), dtype=torch.uint8, device=deriv.device)
+        planes = torch.empty_like(unsm)
+        self._check(_lib.cartb200_sp_planeseg_temporal(self._h, dp, dpitch, lp, lpitch,
+                                                       self.max_label if max_label is None else max_label, pr.ctypes.data,
+                                                       len(prev_planes), refs, unsm.data_ptr(), planes.data_ptr(), self.W,
+                                                       self._stream()))
+        return unsm, planes
+
+    # -- superpixel consumers of the plane fit (SURVEY 8(f) f4) -----------------------------------
+    def label_statistics(self, labels, xyz, n_labels):
+        """countPixels: labels [H,W] u16, xyz [H,W,3] f32 -> (pixel_count, pixel_count_invalid) uint32 [n_labels] (as int32 tensors)."""
+        torch = self.torch
+        _, lp, lpitch, _ = self._img(labels[None], torch.uint16)
+        _, xp, xpitch, _ = self._img(xyz[None], torch.float32, 3)
+        cnt = torch.empty(n_labels, dtype=torch.int32, device=labels.device)
+        inv = torch.empty_like(cnt)
+        self._check(_lib.cartb200_label_statistics(self._h, lp, lpitch, xp, xpitch, n_labels, cnt.data_ptr(), inv.data_ptr(),
+                                                   self._stream()))
+        return cnt, inv
+
+    def region_inliers(self, labels, xyz, n_labels, planes, threshold):
+        """calculateRegionDistance: planes [n_planes][a,b,c,d] (host) -> inliers int32 [n_planes, n_labels]."""
+        torch = self.torch
+        _, lp, lpitch, _ = self._img(labels[None], torch.uint16)
+        _, xp, xpitch, _ = self._img(xyz[None], torch.float32, 3)
+        pl = np.ascontiguousarray(np.asarray(planes, np.float64).reshape(-1, 4))
+        out = torch.empty((pl.shape[0], n_labels), dtype=torch.int32, device=labels.device)
+        self._check(_lib.cartb200_region_inliers(self._h, lp, lpitch, xp, xpitch, n_labels, pl.ctypes.data, pl.shape[0],
+                                                 float(threshold), out.data_ptr(), self._stream()))
+        return out
 
     # -- superpixels -----------------------------------------------------------------------------
     def _slots(self, slots, n):

@@ -499,6 +499,108 @@ int cartb200_sp_planeseg(cartb200_ctx* c, int n, const int16_t* d, size_t dp, si
                               (cudaStream_t)stream);
 }
 
+static int makeTemporalRefs(cartb200_ctx* c, int count, const cartb200_temporal_ref* prev, cb::TemporalRefs& r) {
+    if (count < 0 || count > CARTB200_MAX_TEMPORAL_DISTANCE || (count > 0 && !prev)) {
+        c->err = "temporal vote: previous_count must be 0.." + std::to_string(CARTB200_MAX_TEMPORAL_DISTANCE);
+        return CARTB200_E_ARG;
+    }
+    r = cb::TemporalRefs{};
+    r.count = count;
+    for (int k = 0; k < count; ++k) {
+        if (!prev[k].planes_unsmoothed || !prev[k].optflow || prev[k].planes_pitch < (size_t)c->W ||
+            prev[k].optflow_pitch < (size_t)c->W * 4 || (prev[k].optflow_pitch & 3) || ((uintptr_t)prev[k].optflow & 3)) {
+            c->err = "temporal vote: bad previous frame " + std::to_string(k) + " (optflow is CV_16SC2 with a 4-byte aligned pitch)";
+            return CARTB200_E_ARG;
+        }
+        r.planes[k] = prev[k].planes_unsmoothed;
+        r.planesPitch[k] = prev[k].planes_pitch;
+        r.flow[k] = prev[k].optflow;
+        r.flowPitch[k] = prev[k].optflow_pitch;
+    }
+    return CARTB200_OK;
+}
+
+int cartb200_classify_temporal(cartb200_ctx* c, const int16_t* d, size_t dp, int channels, int channel, const int32_t* paramsHost,
+                               int previousCount, const cartb200_temporal_ref* prev, uint8_t* unsm, uint8_t* smoothed, size_t pp,
+                               void* stream) {
+    if (!c) return CARTB200_E_ARG;
+    if (!d || !unsm || !smoothed || !paramsHost || channels < 1 || channel < 0 || channel >= channels ||
+        dp < (size_t)c->W * 2 * channels || pp < (size_t)c->W) {
+        c->err = "classify_temporal: bad arguments";
+        return CARTB200_E_ARG;
+    }
+    cb::TemporalRefs refs;
+    int rc = makeTemporalRefs(c, previousCount, prev, refs);
+    if (rc) return rc;
+    const cb::PlaneRanges pr{paramsHost[0], paramsHost[1], paramsHost[2], paramsHost[3]};
+    return launch_classify_temporal(c, Img<const int16_t>{d, dp}, channels, channel, pr, refs, Img<uint8_t>{unsm, pp},
+                                    Img<uint8_t>{smoothed, pp}, (cudaStream_t)stream);
+}
+
+int cartb200_sp_planeseg_temporal(cartb200_ctx* c, const int16_t* d, size_t dp, const uint16_t* labels, size_t lp, int maxLabel,
+                                  const int32_t* paramsHost, int previousCount, const cartb200_temporal_ref* prev, uint8_t* unsm,
+                                  uint8_t* planes, size_t pp, void* stream) {
+    if (!c) return CARTB200_E_ARG;
+    if (!c->votes) {
+        c->err = "sp_planeseg_temporal: context created without superpixels";
+        return CARTB200_E_ARG;
+    }
+    if (!d || !labels || !unsm || !planes || !paramsHost || dp < (size_t)c->W * 4 || lp < (size_t)c->W * 2 || pp < (size_t)c->W ||
+        maxLabel < 1 || maxLabel > c->maxLabels) {
+        c->err = "sp_planeseg_temporal: bad arguments";
+        return CARTB200_E_ARG;
+    }
+    if ((size_t)(maxLabel + 1) * 3 * sizeof(uint16_t) > 32768) {  // sp_planeseg.cu:327-331
+        c->err = "Shared memory size exceeds maximum. Reduce image size or increase block size.";
+        return CARTB200_E_UNSUPPORTED;
+    }
+    cb::TemporalRefs refs;
+    int rc = makeTemporalRefs(c, previousCount, prev, refs);
+    if (rc) return rc;
+    const cb::PlaneRanges pr{paramsHost[0], paramsHost[1], paramsHost[2], paramsHost[3]};
+    return launch_sp_planeseg_temporal(c, Img<const int16_t>{d, dp}, Img<const uint16_t>{labels, lp}, maxLabel, pr, refs,
+                                       Img<uint8_t>{unsm, pp}, Img<uint8_t>{planes, pp}, (cudaStream_t)stream);
+}
+
+static int checkLabelDepth(cartb200_ctx* c, const char* what, const uint16_t* labels, size_t lp, const float* xyz, size_t xp,
+                           int nLabels) {
+    if (!c) return CARTB200_E_ARG;
+    if (!labels || !xyz || lp < (size_t)c->W * 2 || xp < (size_t)c->W * 12 || (xp & 3) || nLabels < 1 || nLabels > 65536) {
+        c->err = std::string(what) + ": bad arguments (depth is CV_32FC3 with a pitch that is a multiple of 4)";
+        return CARTB200_E_ARG;
+    }
+    if ((size_t)nLabels * 4 > 32768) {  // planefit.cu:196-199 / :248-251 (the larger of the two shared tables)
+        c->err = std::string(what) + ": Shared memory size exceeds maximum. Was " + std::to_string((size_t)nLabels * 4) +
+                 " but maximum is 32768.";
+        return CARTB200_E_UNSUPPORTED;
+    }
+    return CARTB200_OK;
+}
+
+int cartb200_label_statistics(cartb200_ctx* c, const uint16_t* labels, size_t lp, const float* xyz, size_t xp, int nLabels,
+                              uint32_t* count, uint32_t* invalid, void* stream) {
+    int rc = checkLabelDepth(c, "label_statistics", labels, lp, xyz, xp, nLabels);
+    if (rc) return rc;
+    if (!count || !invalid) {
+        c->err = "label_statistics: null output";
+        return CARTB200_E_ARG;
+    }
+    return launch_label_statistics(c, Img<const uint16_t>{labels, lp}, Img<const float>{xyz, xp}, nLabels, count, invalid,
+                                   (cudaStream_t)stream);
+}
+
+int cartb200_region_inliers(cartb200_ctx* c, const uint16_t* labels, size_t lp, const float* xyz, size_t xp, int nLabels,
+                            const double* planesHost, int nPlanes, double threshold, uint32_t* inliers, void* stream) {
+    int rc = checkLabelDepth(c, "region_inliers", labels, lp, xyz, xp, nLabels);
+    if (rc) return rc;
+    if (!planesHost || nPlanes < 1 || !inliers) {
+        c->err = "region_inliers: bad arguments";
+        return CARTB200_E_ARG;
+    }
+    return launch_region_inliers(c, Img<const uint16_t>{labels, lp}, Img<const float>{xyz, xp}, nLabels, planesHost, nPlanes,
+                                 threshold, inliers, (cudaStream_t)stream);
+}
+
 int cartb200_depth(cartb200_ctx* c, int n, const int16_t* d, size_t dp, size_t dfs, const float* q16Host, float* xyz, size_t xp,
                    size_t xfs, void* stream) {
     int rc = checkBatch(c, n);

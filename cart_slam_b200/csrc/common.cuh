@@ -45,6 +45,22 @@ struct PlaneRanges {
     int hS, hE, vS, vE;
 };
 
+// previous frames of the temporal smoothing vote, passed to the kernels by value
+constexpr int kMaxTemporal = CARTB200_MAX_TEMPORAL_DISTANCE;
+struct TemporalRefs {
+    const uint8_t* planes[kMaxTemporal];  // planes_unsmoothed of frame id-(k+1)
+    const int16_t* flow[kMaxTemporal];    // optflow (CV_16SC2, S10.5) of frame id-k
+    size_t planesPitch[kMaxTemporal], flowPitch[kMaxTemporal];  // bytes
+    int count;
+};
+
+// candidate planes (a, b, c, d) of the region-distance kernel, passed by value in sets of kMaxPlaneSet
+constexpr int kMaxPlaneSet = 16;
+struct PlaneSet {
+    double abcd[kMaxPlaneSet][4];
+    int count;
+};
+
 }  // namespace cb
 
 // The context. Owns every scratch buffer, sized at create time for max_batch frames.
@@ -124,6 +140,10 @@ int launch_classify(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, int c
 int launch_sp_planeseg(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, ImgBatch<const uint16_t> labels, int maxLabel, const int32_t* paramsDev, ImgBatch<uint8_t> unsm, ImgBatch<uint8_t> planes, cudaStream_t s);
 int launch_sp_reset(cartb200_ctx* c, int n, const int* slotsDev, cudaStream_t s);
 int launch_sp_relax(cartb200_ctx* c, int n, const int* slotsDev, int iterations, ImgBatch<const uint8_t> left, ImgBatch<const int16_t> deriv, bool hasDeriv, ImgBatch<uint16_t> out, cudaStream_t s);
+int launch_classify_temporal(cartb200_ctx* c, Img<const int16_t> deriv, int channels, int channel, PlaneRanges pr, const TemporalRefs& refs, Img<uint8_t> unsm, Img<uint8_t> smoothed, cudaStream_t s);
+int launch_sp_planeseg_temporal(cartb200_ctx* c, Img<const int16_t> deriv, Img<const uint16_t> labels, int maxLabel, PlaneRanges pr, const TemporalRefs& refs, Img<uint8_t> unsm, Img<uint8_t> planes, cudaStream_t s);
+int launch_label_statistics(cartb200_ctx* c, Img<const uint16_t> labels, Img<const float> xyz, int nLabels, uint32_t* count, uint32_t* invalid, cudaStream_t s);
+int launch_region_inliers(cartb200_ctx* c, Img<const uint16_t> labels, Img<const float> xyz, int nLabels, const double* planesHost, int nPlanes, double threshold, uint32_t* inliers, cudaStream_t s);
 int launch_depth(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<float> xyz, const float* q16Host, cudaStream_t s);
 int launch_border_map(cartb200_ctx* c, Img<const uint16_t> labels, Img<uint8_t> border, cudaStream_t s);
 void build_sp_tile_tables(int W, int H, std::vector<int>& tileMap, std::vector<uint32_t>& tab);

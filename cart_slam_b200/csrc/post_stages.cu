@@ -313,6 +313,175 @@ int launch_sp_planeseg(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, Im
 }
 
 // ---------------------------------------------------------------------------------------------
+// Temporal smoothing vote: the per-pixel loop of classifyPlanes
+// (/root/reference/src/modules/planeseg/planeseg.cu:199-240, MODE 0) and of performSuperPixelClassifications
+// (/root/reference/src/modules/planeseg/sp_planeseg.cu:79-117, MODE 1).  refs.planes[k] = "planes_unsmoothed" of
+// frame id-(k+1), refs.flow[k] = "optflow" (CV_16SC2, S10.5) of frame id-k.  Every flow image is read at the CURRENT
+// pixel (one coalesced 32-bit load per reference frame), the position walks back by the accumulated integer flow,
+// out-of-image positions are skipped but stay accumulated.  The three vote counters live in the bytes of one
+// register.  Streaming work: 4 B (flow) + 1 B (gathered plane) per reference frame and pixel -> HBM/latency-bound.
+template <int MODE>
+__device__ __forceinline__ uint8_t temporal_vote(const TemporalRefs& r, uint8_t plane, int px, int py, int W, int H) {
+    unsigned votes = (MODE ? 2u : 1u) << (8 * plane);
+    int x = px, y = py;
+#pragma unroll 1
+    for (int k = 0; k < r.count; ++k) {
+        const int fl = __ldg(reinterpret_cast<const int*>(reinterpret_cast<const char*>(r.flow[k]) + (size_t)py * r.flowPitch[k]) + px);
+        x -= (int)(int16_t)(fl & 0xFFFF) >> 5;
+        y -= (fl >> 16) >> 5;
+        if (x < 0 || y < 0 || x >= W || y >= H) continue;
+        const unsigned v = __ldg(r.planes[k] + (size_t)y * r.planesPitch[k] + x);
+        if (v <= 2u) votes += 1u << (8 * v);  // the reference indexes votes[] with the stored value; > 2 is out of contract
+    }
+    const unsigned vh = votes & 0xFFu, vv = (votes >> 8) & 0xFFu, vu = (votes >> 16) & 0xFFu;
+    const unsigned best = vh > vv ? (unsigned)CARTB200_PLANE_HORIZONTAL : (unsigned)CARTB200_PLANE_VERTICAL;
+    const unsigned vb = vh > vv ? vh : vv;
+    if (MODE == 0) return vb == 0 ? CARTB200_PLANE_UNKNOWN : (uint8_t)best;
+    return vb < vu ? CARTB200_PLANE_UNKNOWN : (uint8_t)best;
+}
+
+__global__ void __launch_bounds__(256) classify_temporal_kernel(Img<const int16_t> deriv, int channels, int channel, PlaneRanges pr,
+                                                                TemporalRefs refs, Img<uint8_t> unsm, Img<uint8_t> smoothed,
+                                                                int W, int H) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int16_t d = __ldg(deriv.row(y) + (size_t)x * channels + channel);
+    const uint8_t p = classify_one(d, pr.hS, pr.hE, pr.vS, pr.vE);
+    unsm.at(x, y) = p;
+    smoothed.at(x, y) = refs.count > 0 ? temporal_vote<0>(refs, p, x, y, W, H) : p;
+}
+
+int launch_classify_temporal(cartb200_ctx* c, Img<const int16_t> deriv, int channels, int channel, PlaneRanges pr,
+                             const TemporalRefs& refs, Img<uint8_t> unsm, Img<uint8_t> smoothed, cudaStream_t s) {
+    dim3 grid(ceilDiv(c->W, 256), c->H, 1);
+    classify_temporal_kernel<<<grid, 256, 0, s>>>(deriv, channels, channel, pr, refs, unsm, smoothed, c->W, c->H);
+    CB_LAUNCH_CHECK(c);
+    return CARTB200_OK;
+}
+
+// performSuperPixelClassifications with previousPlanesCount > 0: the voted plane (not the unsmoothed class) feeds
+// the per-superpixel counters; "planes_unsmoothed" still holds the range-rule class (sp_planeseg.cu:77).
+__global__ void __launch_bounds__(256) sp_vote_temporal_kernel(Img<const int16_t> deriv, Img<const uint16_t> labels, int maxLabel,
+                                                               PlaneRanges pr, TemporalRefs refs, Img<uint8_t> unsm,
+                                                               uint32_t* __restrict__ votes, int W, int H) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const bool in = x < W;
+    unsigned key = 0xFFFFFFFFu;
+    if (in) {
+        const int16_t d = __ldg(deriv.row(y) + 2 * (size_t)x);
+        uint8_t p = classify_one(d, pr.hS, pr.hE, pr.vS, pr.vE);
+        unsm.at(x, y) = p;
+        if (refs.count > 0) p = temporal_vote<1>(refs, p, x, y, W, H);
+        const unsigned l = __ldg(labels.row(y) + x);
+        if ((int)l < maxLabel) key = l * 4 + p;
+    }
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, key);
+    if (key != 0xFFFFFFFFu && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&votes[key], (unsigned)__popc(peers));
+}
+
+int launch_sp_planeseg_temporal(cartb200_ctx* c, Img<const int16_t> deriv, Img<const uint16_t> labels, int maxLabel, PlaneRanges pr,
+                                const TemporalRefs& refs, Img<uint8_t> unsm, Img<uint8_t> planes, cudaStream_t s) {
+    const int voteStride = c->maxLabels * 4;
+    CB_CHECK_CUDA(c, cudaMemsetAsync(c->votes, 0, (size_t)voteStride * sizeof(uint32_t), s));
+    dim3 grid(ceilDiv(c->W, 256), c->H, 1);
+    sp_vote_temporal_kernel<<<grid, 256, 0, s>>>(deriv, labels, maxLabel, pr, refs, unsm, c->votes, c->W, c->H);
+    CB_LAUNCH_CHECK(c);
+    sp_assign_kernel<<<grid, 256, 0, s>>>(ImgBatch<const uint16_t>{labels.data, labels.pitch, 0}, maxLabel, c->votes, voteStride,
+                                          ImgBatch<uint8_t>{planes.data, planes.pitch, 0}, c->W, c->H);
+    CB_LAUNCH_CHECK(c);
+    return CARTB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Superpixel consumers of the plane fit.
+// countPixels, /root/reference/src/modules/planefit.cu:38-83: per label the pixel count and the number of pixels with
+// an invalid depth Z (IS_VALID_DEPTH :19).  calculateRegionDistance, :85-138 with calculateDistanceFromPlane :34-36:
+// per (plane, label) the number of valid pixels closer than `threshold` to the plane, in double precision with the
+// reference's operation order (this library is compiled without FMA contraction, like the oracle).
+// One thread per pixel; lanes of a warp that carry the same label are merged (__match_any_sync once per pixel, then
+// one ballot per counter) so a 12x12-block superpixel costs ~3 atomics per warp row instead of 32.
+__device__ __forceinline__ bool valid_depth(float z) { return isfinite(z) && (double)z <= 40.0 && (double)z > 0.0; }
+
+__global__ void __launch_bounds__(256) label_statistics_kernel(Img<const uint16_t> labels, Img<const float> xyz, int nLabels,
+                                                               uint32_t* __restrict__ count, uint32_t* __restrict__ invalid, int W,
+                                                               int H) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    unsigned key = 0xFFFFFFFFu;
+    bool inv = false;
+    if (x < W) {
+        const unsigned l = __ldg(labels.row(y) + x);
+        if ((int)l < nLabels) {
+            key = l;
+            inv = !valid_depth(__ldg(xyz.row(y) + 3 * (size_t)x + 2));
+        }
+    }
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, key);
+    const unsigned invMask = __ballot_sync(active, inv) & peers;
+    if (key != 0xFFFFFFFFu && (threadIdx.x & 31) == (__ffs(peers) - 1)) {
+        atomicAdd(&count[key], (unsigned)__popc(peers));
+        if (invMask) atomicAdd(&invalid[key], (unsigned)__popc(invMask));
+    }
+}
+
+int launch_label_statistics(cartb200_ctx* c, Img<const uint16_t> labels, Img<const float> xyz, int nLabels, uint32_t* count,
+                            uint32_t* invalid, cudaStream_t s) {
+    CB_CHECK_CUDA(c, cudaMemsetAsync(count, 0, (size_t)nLabels * sizeof(uint32_t), s));
+    CB_CHECK_CUDA(c, cudaMemsetAsync(invalid, 0, (size_t)nLabels * sizeof(uint32_t), s));
+    dim3 grid(ceilDiv(c->W, 256), c->H, 1);
+    label_statistics_kernel<<<grid, 256, 0, s>>>(labels, xyz, nLabels, count, invalid, c->W, c->H);
+    CB_LAUNCH_CHECK(c);
+    return CARTB200_OK;
+}
+
+__global__ void __launch_bounds__(256) region_inliers_kernel(Img<const uint16_t> labels, Img<const float> xyz, int nLabels,
+                                                             PlaneSet ps, double threshold, uint32_t* __restrict__ inliers, int W,
+                                                             int H) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    unsigned key = 0xFFFFFFFFu;
+    double X = 0.0, Y = 0.0, Z = 0.0;
+    bool ok = false;
+    if (x < W) {
+        const unsigned l = __ldg(labels.row(y) + x);
+        if ((int)l < nLabels) {
+            key = l;
+            const float* q = xyz.row(y) + 3 * (size_t)x;
+            const float fz = __ldg(q + 2);
+            ok = valid_depth(fz);
+            X = (double)__ldg(q);
+            Y = (double)__ldg(q + 1);
+            Z = (double)fz;
+        }
+    }
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, key);
+    const bool leader = key != 0xFFFFFFFFu && (threadIdx.x & 31) == (__ffs(peers) - 1);
+#pragma unroll 1
+    for (int p = 0; p < ps.count; ++p) {
+        const double a = ps.abcd[p][0], b = ps.abcd[p][1], cc = ps.abcd[p][2], d = ps.abcd[p][3];
+        const double dist = fabs(a * X + b * Y + cc * Z + d) / sqrt(a * a + b * b + cc * cc);
+        const unsigned hit = __ballot_sync(active, ok && dist < threshold) & peers;
+        if (leader && hit) atomicAdd(&inliers[(size_t)p * nLabels + key], (unsigned)__popc(hit));
+    }
+}
+
+int launch_region_inliers(cartb200_ctx* c, Img<const uint16_t> labels, Img<const float> xyz, int nLabels, const double* planesHost,
+                          int nPlanes, double threshold, uint32_t* inliers, cudaStream_t s) {
+    CB_CHECK_CUDA(c, cudaMemsetAsync(inliers, 0, (size_t)nPlanes * nLabels * sizeof(uint32_t), s));
+    dim3 grid(ceilDiv(c->W, 256), c->H, 1);
+    for (int p0 = 0; p0 < nPlanes; p0 += kMaxPlaneSet) {
+        PlaneSet ps;
+        ps.count = nPlanes - p0 < kMaxPlaneSet ? nPlanes - p0 : kMaxPlaneSet;
+        for (int i = 0; i < ps.count; ++i)
+            for (int j = 0; j < 4; ++j) ps.abcd[i][j] = planesHost[4 * (p0 + i) + j];
+        region_inliers_kernel<<<grid, 256, 0, s>>>(labels, xyz, nLabels, ps, threshold, inliers + (size_t)p0 * nLabels, c->W, c->H);
+        CB_LAUNCH_CHECK(c);
+    }
+    return CARTB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // DepthModule::runInternal, /root/reference/src/modules/depth.cpp:9-25: disparity * (1/16) as float, then the
 // third-party cv::cuda::reprojectImageTo3D(Q, 3 channels).  Normative arithmetic: oracle/stages.cpp orc_depth
 // (single precision, same operation order; compiled without FMA contraction).  12 B written per pixel: HBM-bound.

@@ -7,9 +7,12 @@
 //   PlaneParameters / providers                   /root/reference/include/modules/planeseg.hpp:25-113
 //   DisparityPlaneSegmentationModule              /root/reference/include/modules/planeseg.hpp:115-162
 //   SuperPixelDisparityPlaneSegmentationModule    /root/reference/include/modules/planeseg.hpp:164-186
-// Temporal smoothing (optical flow) is outside the hot-path scope: requesting it throws.
+// Temporal smoothing is supported when some module provides the "optflow" key (CV_16SC2, S10.5):
+// the reference's producer is the NVOFA hardware engine behind OpenCV (out of scope); ExternalOpticalFlowModule below is
+// the hook an integrator replaces with a real flow source.
 #pragma once
 #include <cmath>
+#include <functional>
 
 #include "cart/core.hpp"
 
@@ -24,6 +27,7 @@ struct cartb200_ctx;
 #define CARTSLAM_KEY_PLANES "planes"
 #define CARTSLAM_KEY_PLANES_UNSMOOTHED "planes_unsmoothed"
 #define CARTSLAM_KEY_PLANE_PARAMETERS "plane_parameters"
+#define CARTSLAM_KEY_OPTFLOW "optflow" /* /root/reference/include/modules/optflow.hpp:13 */
 #define CARTSLAM_KEY_DISPARITY_DERIVATIVE_HIST "disp_derivative_histogram"
 #define CARTSLAM_DISPARITY_INVALID (-32768)
 #define CARTSLAM_PLANE_COUNT 3
@@ -33,6 +37,7 @@ namespace cart {
 
 typedef int16_t disparity_t;
 typedef int16_t derivative_t;
+typedef int16_t optical_flow_t;  // S10.5 fixed point, two channels (/root/reference/include/modules/optflow.hpp:17)
 namespace contour {
 typedef uint16_t label_t;
 }
@@ -135,6 +140,28 @@ class StaticPlaneParameterProvider : public PlaneParameterProvider {
     void updatePlaneParameters(System&, SystemRunData&, const std::vector<int32_t>&) override {}
 };
 
+// Stand-in for ImageOpticalFlowModule (/root/reference/src/modules/optflow.cpp:52-134): provides "optflow" for every
+// frame after the first (a null entry for frame 1, like the reference, :119-121) from a user callback that fills a
+// host CV_16SC2 image (rows x cols x 2 int16, S10.5).  The default callback writes a constant flow.
+class ExternalOpticalFlowModule : public SyncWrapperSystemModule {
+   public:
+    typedef std::function<void(uint32_t id, int rows, int cols, optical_flow_t* flowXY)> flow_fn_t;
+    explicit ExternalOpticalFlowModule(flow_fn_t fn);
+    ExternalOpticalFlowModule(double flowX, double flowY);  // constant flow in pixels
+    system_data_t runInternal(System& system, SystemRunData& data) override;
+
+   private:
+    flow_fn_t fn;
+};
+
+// previousPlanes / previousOpticalFlow lists of the temporal vote (planeseg.cu:300-343, sp_planeseg.cu:256-316);
+// keeps the images alive until the kernel that reads them has finished.
+struct TemporalHistory {
+    std::vector<std::shared_ptr<image_t>> planes, flows;
+    int count() const { return (int)planes.size(); }
+};
+TemporalHistory collectTemporalHistory(SystemRunData& data, unsigned int distance);
+
 class DisparityPlaneSegmentationModule : public SyncWrapperSystemModule {
    public:
     DisparityPlaneSegmentationModule(std::shared_ptr<PlaneParameterProvider> planeParameterProvider, const int updateInterval = 30,
@@ -145,6 +172,8 @@ class DisparityPlaneSegmentationModule : public SyncWrapperSystemModule {
    private:
     void updatePlaneParameters(System& system, SystemRunData& data);
     const int updateInterval, resetInterval;
+    const bool useTemporalSmoothing;
+    const unsigned int temporalSmoothingDistance;
     std::shared_ptr<PlaneParameterProvider> planeParameterProvider;
     std::unique_ptr<Kernels> kernels;
     std::mutex derivativeHistogramMutex;
@@ -162,6 +191,8 @@ class SuperPixelDisparityPlaneSegmentationModule : public SyncWrapperSystemModul
    private:
     void updatePlaneParameters(System& system, SystemRunData& data);
     const int updateInterval, resetInterval;
+    const bool useTemporalSmoothing;
+    const unsigned int temporalSmoothingDistance;
     std::shared_ptr<PlaneParameterProvider> planeParameterProvider;
     std::unique_ptr<Kernels> kernels;
     std::mutex derivativeHistogramMutex;
@@ -173,7 +204,8 @@ class SuperPixelDisparityPlaneSegmentationModule : public SyncWrapperSystemModul
 namespace config {
 // Module types outside the hot-path scope (visualisation, optflow, depth, features, planefit, ...) are
 // rejected with std::runtime_error unless skipOutOfScope is set, in which case they are skipped with a warning
-// and `use_temporal_smoothing` is forced off.
+// (and `use_temporal_smoothing` is forced off when no module provides "optflow").  Extra type of this build:
+// {"type": "external_optflow", "flow_x": px, "flow_y": px} -> ExternalOpticalFlowModule with a constant flow.
 void applyModuleConfigText(const std::string& jsonText, std::shared_ptr<System> system, bool skipOutOfScope = false);
 void readModuleConfig(const std::string& path, std::shared_ptr<System> system, bool skipOutOfScope = false);
 }  // namespace config

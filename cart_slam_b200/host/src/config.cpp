@@ -49,6 +49,9 @@ void applyModuleConfigText(const std::string& text, std::shared_ptr<System> syst
     const json modules = json::parse(text);
     if (!modules.is_array()) throw std::runtime_error("Modules configuration is not an array.");
     const Size size = system->getDataSource()->getImageSize();
+    bool haveFlow = false;
+    for (const auto& m : modules)
+        if (m.is_object() && m.value("type", std::string()) == "external_optflow") haveFlow = true;
     for (const auto& m : modules) {
         if (!m.is_object()) throw std::runtime_error("Module configuration is not an object.");
         const std::string type = m.at("type").get<std::string>();
@@ -66,11 +69,14 @@ void applyModuleConfigText(const std::string& text, std::shared_ptr<System> syst
             system->addModule<ImageDisparityDerivativeModule>();
         } else if (type == "depth") {
             system->addModule<DepthModule>();
+        } else if (type == "external_optflow") {  // this build's stand-in for the NVOFA "optflow" module
+            system->addModule<ExternalOpticalFlowModule>(get(m, "flow_x", 0.0), get(m, "flow_y", 0.0));
+            haveFlow = true;
         } else if (type == "disparity_planeseg" || type == "superpixel_disparity_planeseg") {
             auto provider = readParameterProvider(m.at("parameter_provider"));
             bool temporal = get(m, "use_temporal_smoothing", false);
-            if (temporal && skipOutOfScope) {
-                CART_LOG_WARN("config", type + ": use_temporal_smoothing needs optical flow (out of scope) - disabled");
+            if (temporal && skipOutOfScope && !haveFlow) {
+                CART_LOG_WARN("config", type + ": use_temporal_smoothing needs a module that provides optflow - disabled");
                 temporal = false;
             }
             const int update = get(m, "update_interval", 30), reset = get(m, "reset_interval", 10);

@@ -199,20 +199,85 @@ void HistogramPeakPlaneParameterProvider::updatePlaneParameters(System&, SystemR
     verticalRange = {p[4], p[5]};
 }
 
-static void rejectTemporal(bool use) {
-    if (use)
-        throw std::runtime_error(
-            "use_temporal_smoothing needs the optical-flow module, which is outside the scope of the B200 hot path");
+// ---- temporal smoothing support --------------------------------------------------------
+static void checkTemporalDistance(bool use, unsigned int distance) {
+    if (use && (distance < 1 || distance > CARTB200_MAX_TEMPORAL_DISTANCE))
+        throw std::runtime_error("temporal_smoothing_distance must be 1.." + std::to_string(CARTB200_MAX_TEMPORAL_DISTANCE));
+}
+
+// the dependency list of planeseg.hpp:128-137 / sp_planeseg.cu:200-209
+static void addTemporalDependencies(std::vector<module_dependency_t>& requiresData, unsigned int distance) {
+    requiresData.push_back(module_dependency_t(CARTSLAM_KEY_OPTFLOW));
+    for (unsigned int i = 1; i <= distance; i++) {
+        requiresData.push_back(module_dependency_t(CARTSLAM_KEY_PLANES_UNSMOOTHED, -(int)i));
+        if ((i + 1) <= distance) requiresData.push_back(module_dependency_t(CARTSLAM_KEY_OPTFLOW, -(int)i));
+    }
+}
+
+// planeseg.cu:300-337 / sp_planeseg.cu:256-310: entry k = planes_unsmoothed of run id-(k+1) and optflow of run id-k
+TemporalHistory collectTemporalHistory(SystemRunData& data, unsigned int distance) {
+    TemporalHistory h;
+    if (data.id <= 1) return h;
+    std::shared_ptr<image_t> flow = data.getData<image_t>(CARTSLAM_KEY_OPTFLOW);
+    for (int i = 1; i <= (int)distance; i++) {
+        if ((int)data.id - i <= 0) break;
+        auto relativeRun = data.getRelativeRun((int8_t)-i);
+        auto prev = relativeRun->getData<image_t>(CARTSLAM_KEY_PLANES_UNSMOOTHED);  // blocks until available
+        if (!flow || flow->empty() || flow->type != IMG_16SC2) throw std::runtime_error("optflow must be a CV_16SC2 image");
+        h.planes.push_back(prev);
+        h.flows.push_back(flow);
+        flow.reset();
+        if (relativeRun->id > 1 && h.count() < (int)distance) flow = relativeRun->getData<image_t>(CARTSLAM_KEY_OPTFLOW);
+    }
+    return h;
+}
+
+static std::vector<cartb200_temporal_ref> temporalRefs(const TemporalHistory& h) {
+    std::vector<cartb200_temporal_ref> refs(h.count());
+    for (int k = 0; k < h.count(); ++k)
+        refs[k] = {h.planes[k]->as<uint8_t>(), h.planes[k]->pitch, h.flows[k]->as<int16_t>(), h.flows[k]->pitch};
+    return refs;
+}
+
+ExternalOpticalFlowModule::ExternalOpticalFlowModule(flow_fn_t fn) : SyncWrapperSystemModule("ExternalOpticalFlow"), fn(std::move(fn)) {
+    providesData.push_back(CARTSLAM_KEY_OPTFLOW);
+}
+
+ExternalOpticalFlowModule::ExternalOpticalFlowModule(double flowX, double flowY)
+    : ExternalOpticalFlowModule([flowX, flowY](uint32_t, int rows, int cols, optical_flow_t* out) {
+          const optical_flow_t fx = (optical_flow_t)std::lrint(flowX * 32.0), fy = (optical_flow_t)std::lrint(flowY * 32.0);
+          for (size_t i = 0; i < (size_t)rows * cols; ++i) {
+              out[2 * i] = fx;
+              out[2 * i + 1] = fy;
+          }
+      }) {}
+
+system_data_t ExternalOpticalFlowModule::runInternal(System&, SystemRunData& data) {
+    if (data.id <= 1) return MODULE_RETURN(CARTSLAM_KEY_OPTFLOW, std::shared_ptr<void>());  // optflow.cpp:119-121
+    const image_t reference = getReferenceImage(data.dataElement);
+    std::vector<optical_flow_t> host((size_t)reference.rows * reference.cols * 2);
+    fn(data.id, reference.rows, reference.cols, host.data());
+    image_t flow(reference.rows, reference.cols, IMG_16SC2);
+    flow.upload(host.data(), (size_t)reference.cols * 2 * sizeof(optical_flow_t));
+    syncStream(nullptr);
+    return MODULE_RETURN_SHARED(CARTSLAM_KEY_OPTFLOW, image_t, flow);
 }
 
 // ---- DisparityPlaneSegmentationModule (planeseg.cu:246-403) ----------------------------------------------
 DisparityPlaneSegmentationModule::DisparityPlaneSegmentationModule(std::shared_ptr<PlaneParameterProvider> provider, const int updateInterval,
                                                                    const int resetInterval, const bool useTemporalSmoothing,
-                                                                   const unsigned int)
-    : SyncWrapperSystemModule("PlaneSegmentation"), updateInterval(updateInterval), resetInterval(resetInterval), planeParameterProvider(provider) {
-    rejectTemporal(useTemporalSmoothing);
+                                                                   const unsigned int temporalSmoothingDistance)
+    : SyncWrapperSystemModule("PlaneSegmentation"),
+      updateInterval(updateInterval),
+      resetInterval(resetInterval),
+      useTemporalSmoothing(useTemporalSmoothing),
+      temporalSmoothingDistance(temporalSmoothingDistance),
+      planeParameterProvider(provider) {
+    checkTemporalDistance(useTemporalSmoothing, temporalSmoothingDistance);
     requiresData.push_back(module_dependency_t(CARTSLAM_KEY_DISPARITY));
+    if (useTemporalSmoothing) addTemporalDependencies(requiresData, temporalSmoothingDistance);  // planeseg.hpp:128-137
     providesData.push_back(CARTSLAM_KEY_PLANES);
+    if (useTemporalSmoothing) providesData.push_back(CARTSLAM_KEY_PLANES_UNSMOOTHED);  // planeseg.hpp:141-143
 }
 
 system_data_t DisparityPlaneSegmentationModule::runInternal(System& system, SystemRunData& data) {
@@ -241,6 +306,23 @@ system_data_t DisparityPlaneSegmentationModule::runInternal(System& system, Syst
     updatePlaneParameters(system, data);
     const PlaneParameters p = planeParameterProvider->getPlaneParameters();
     const int32_t params[4] = {p.horizontalRange.first, p.horizontalRange.second, p.verticalRange.first, p.verticalRange.second};
+    if (useTemporalSmoothing) {  // planeseg.cu:300-376
+        const TemporalHistory history = collectTemporalHistory(data, temporalSmoothingDistance);
+        const std::vector<cartb200_temporal_ref> refs = temporalRefs(history);
+        image_t smoothed(disparity->rows, disparity->cols, IMG_8UC1);
+        if (smoothed.pitch != planes.pitch) throw std::runtime_error("plane image pitch mismatch");
+        kernels->check(cartb200_classify_temporal(kernels->get(), derivatives.as<int16_t>(), derivatives.pitch, 1, 0, params, history.count(),
+                                                  refs.data(), planes.as<uint8_t>(), smoothed.as<uint8_t>(), planes.pitch, st.s),
+                       "DisparityPlaneSegmentationModule classify (temporal)");
+        st.sync();
+        if (data.id == 1) {  // both keys name the same image on the first run (planeseg.cu:361-368)
+            auto ptr = std::shared_ptr<void>(std::make_shared<image_t>(planes));
+            return MODULE_RETURN_ALL(std::make_pair(std::string(CARTSLAM_KEY_PLANES), ptr),
+                                     std::make_pair(std::string(CARTSLAM_KEY_PLANES_UNSMOOTHED), ptr));
+        }
+        return MODULE_RETURN_ALL(MODULE_MAKE_PAIR(CARTSLAM_KEY_PLANES, image_t, smoothed),
+                                 MODULE_MAKE_PAIR(CARTSLAM_KEY_PLANES_UNSMOOTHED, image_t, planes));
+    }
     kernels->check(cartb200_classify(kernels->get(), 1, derivatives.as<int16_t>(), derivatives.pitch, 0, 1, 0, params, planes.as<uint8_t>(),
                                      planes.pitch, 0, st.s),
                    "DisparityPlaneSegmentationModule classify");
@@ -265,13 +347,20 @@ void DisparityPlaneSegmentationModule::updatePlaneParameters(System& system, Sys
 // ---- SuperPixelDisparityPlaneSegmentationModule (sp_planeseg.cu:188-388) ---------------------------------
 SuperPixelDisparityPlaneSegmentationModule::SuperPixelDisparityPlaneSegmentationModule(std::shared_ptr<PlaneParameterProvider> provider,
                                                                                        const int updateInterval, const int resetInterval,
-                                                                                       const bool useTemporalSmoothing, const unsigned int)
-    : SyncWrapperSystemModule("SPPlaneSegmentation"), updateInterval(updateInterval), resetInterval(resetInterval), planeParameterProvider(provider) {
-    rejectTemporal(useTemporalSmoothing);
+                                                                                       const bool useTemporalSmoothing,
+                                                                                       const unsigned int temporalSmoothingDistance)
+    : SyncWrapperSystemModule("SPPlaneSegmentation"),
+      updateInterval(updateInterval),
+      resetInterval(resetInterval),
+      useTemporalSmoothing(useTemporalSmoothing),
+      temporalSmoothingDistance(temporalSmoothingDistance),
+      planeParameterProvider(provider) {
+    checkTemporalDistance(useTemporalSmoothing, temporalSmoothingDistance);
     requiresData.push_back(module_dependency_t(CARTSLAM_KEY_SUPERPIXELS));
     requiresData.push_back(module_dependency_t(CARTSLAM_KEY_SUPERPIXELS_MAX_LABEL));
     requiresData.push_back(module_dependency_t(CARTSLAM_KEY_DISPARITY_DERIVATIVE));
     requiresData.push_back(module_dependency_t(CARTSLAM_KEY_DISPARITY_DERIVATIVE_HISTOGRAM));
+    if (useTemporalSmoothing) addTemporalDependencies(requiresData, temporalSmoothingDistance);  // sp_planeseg.cu:200-209
     providesData.push_back(CARTSLAM_KEY_PLANES);
     providesData.push_back(CARTSLAM_KEY_PLANES_UNSMOOTHED);
 }
@@ -297,7 +386,16 @@ system_data_t SuperPixelDisparityPlaneSegmentationModule::runInternal(System& sy
             kernels.reset(new Kernels(derivatives->size(), false, true, 4, 256, -1, 5, bs));
         }
     }
-    {
+    if (useTemporalSmoothing) {  // sp_planeseg.cu:256-345
+        const TemporalHistory history = collectTemporalHistory(data, temporalSmoothingDistance);
+        const std::vector<cartb200_temporal_ref> refs = temporalRefs(history);
+        std::lock_guard<std::mutex> lock(kernels->mutex);
+        kernels->check(cartb200_sp_planeseg_temporal(kernels->get(), derivatives->as<int16_t>(), derivatives->pitch, labels->as<uint16_t>(),
+                                                     labels->pitch, maxLabel, params, history.count(), refs.data(), planes.as<uint8_t>(),
+                                                     smoothed.as<uint8_t>(), planes.pitch, st.s),
+                       "SuperPixelDisparityPlaneSegmentationModule (temporal)");
+        st.sync();
+    } else {
         std::lock_guard<std::mutex> lock(kernels->mutex);
         kernels->check(cartb200_sp_planeseg(kernels->get(), 1, derivatives->as<int16_t>(), derivatives->pitch, 0, labels->as<uint16_t>(),
                                             labels->pitch, 0, maxLabel, params, planes.as<uint8_t>(), smoothed.as<uint8_t>(), planes.pitch, 0,

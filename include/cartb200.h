@@ -176,6 +176,50 @@ int cartb200_sp_planeseg(cartb200_ctx* ctx, int n, const int16_t* derivative, si
                          uint8_t* planes_unsmoothed, uint8_t* planes, size_t planes_pitch, size_t planes_frame_stride,
                          void* stream);
 
+/* ---- temporal smoothing vote -----------------------------------------------
+ * Replaces the previousPlanesCount > 0 branch of classifyPlanes
+ * (/root/reference/src/modules/planeseg/planeseg.cu:160-243, vote :199-240) and of performSuperPixelClassifications
+ * (/root/reference/src/modules/planeseg/sp_planeseg.cu:25-134, vote :79-117).  The reference hands its kernels two
+ * device arrays of cv_mat_ptr_t {data, step} (/root/reference/include/utils/cuda.cuh:47-51) filled by the module
+ * (planeseg.cu:300-343, sp_planeseg.cu:256-316); here the same list is a HOST array, entry k =
+ *   planes_unsmoothed of frame id-(k+1)  ("planes_unsmoothed", CV_8UC1, values 0..2)  and
+ *   optflow           of frame id-k      ("optflow", CV_16SC2, S10.5 fixed point; pitch a multiple of 4).
+ * The optical flow itself is produced outside this library (the reference uses the NVOFA engine through OpenCV,
+ * /root/reference/src/modules/optflow.cpp:58-70).  previous_count == 0 (frame id 1): smoothed = unsmoothed, as the
+ * module returns one image under both keys (planeseg.cu:361-368).  One frame per call: the module surface is
+ * per-frame; all images of a call share the context's W x H. */
+#define CARTB200_MAX_TEMPORAL_DISTANCE 8
+typedef struct cartb200_temporal_ref {
+    const uint8_t* planes_unsmoothed;
+    size_t planes_pitch;
+    const int16_t* optflow;
+    size_t optflow_pitch;
+} cartb200_temporal_ref;
+int cartb200_classify_temporal(cartb200_ctx* ctx, const int16_t* derivative, size_t deriv_pitch, int channels, int channel,
+                               const int32_t* params_host /* 4 */, int previous_count,
+                               const cartb200_temporal_ref* previous_host, uint8_t* planes_unsmoothed,
+                               uint8_t* planes_smoothed, size_t planes_pitch, void* stream);
+int cartb200_sp_planeseg_temporal(cartb200_ctx* ctx, const int16_t* derivative, size_t deriv_pitch, const uint16_t* labels,
+                                  size_t labels_pitch, int max_label, const int32_t* params_host /* 4 */,
+                                  int previous_count, const cartb200_temporal_ref* previous_host,
+                                  uint8_t* planes_unsmoothed, uint8_t* planes, size_t planes_pitch, void* stream);
+
+/* ---- superpixel consumers of the plane fit ------------------------------------
+ * label_statistics replaces countPixels (/root/reference/src/modules/planefit.cu:38-83, called from
+ * generateLabelStatistics :182-209): pixel_count[l], pixel_count_invalid[l] for l < n_labels (= maxLabelId + 1),
+ * DEVICE uint32 arrays (the reference's label_statistics_t holds two uint16, /root/reference/include/modules/planefit.hpp:20-23,
+ * updated by a 16-bit atomic that is not carry-safe; counts here are exact).
+ * region_inliers replaces calculateRegionDistance (planefit.cu:85-138, called from attemptAssignment :211-275):
+ * inliers[p * n_labels + l] = valid-depth pixels of label l closer than `threshold` to plane p.
+ * planes_host: n_planes x {a, b, c, d} doubles on the HOST (plane_t, planefit.cu:27-32).
+ * depth: CV_32FC3 "depth" image (X, Y, Z), pitch a multiple of 4. */
+int cartb200_label_statistics(cartb200_ctx* ctx, const uint16_t* labels, size_t labels_pitch, const float* depth,
+                              size_t depth_pitch, int n_labels, uint32_t* pixel_count, uint32_t* pixel_count_invalid,
+                              void* stream);
+int cartb200_region_inliers(cartb200_ctx* ctx, const uint16_t* labels, size_t labels_pitch, const float* depth,
+                            size_t depth_pitch, int n_labels, const double* planes_host, int n_planes, double threshold,
+                            uint32_t* inliers, void* stream);
+
 /* ---- depth (the stage right after disparity) ------------------------------
  * Replaces DepthModule::runInternal (/root/reference/src/modules/depth.cpp:9-25): convertTo(CV_32F, 1/16) +
  * cv::cuda::reprojectImageTo3D(disparityFloat, depth, Q, 3).  q16_host: the 4x4 reprojection matrix Q

@@ -29,6 +29,18 @@ int orc_naive_derivative(const int16_t* disp, int W, int H, int16_t* deriv, int3
 int orc_classify(const int16_t* deriv, long n, int stride, int hS, int hE, int vS, int vE, uint8_t* planes);
 int orc_sp_planeseg(const int16_t* deriv2, const uint16_t* labels, int W, int H, int maxLabel, int hS, int hE, int vS,
                     int vE, uint8_t* planesUnsmoothed, uint8_t* planes);
+/* temporal smoothing vote: planeseg.cu:199-240 / sp_planeseg.cu:79-117 */
+int orc_classify_temporal(const int16_t* deriv, int W, int H, int stride, int hS, int hE, int vS, int vE, int count,
+                          const uint8_t* const* prevPlanes, const int16_t* const* prevFlow, uint8_t* planesUnsmoothed,
+                          uint8_t* planesSmoothed);
+int orc_sp_planeseg_temporal(const int16_t* deriv2, const uint16_t* labels, int W, int H, int maxLabel, int hS, int hE,
+                             int vS, int vE, int count, const uint8_t* const* prevPlanes, const int16_t* const* prevFlow,
+                             uint8_t* planesUnsmoothed, uint8_t* planes);
+/* superpixel consumers of the plane fit: countPixels / calculateRegionDistance, planefit.cu:38-138 */
+int orc_label_statistics(const uint16_t* labels, const float* xyz, int W, int H, int nLabels, uint32_t* pixelCount,
+                         uint32_t* pixelCountInvalid);
+int orc_region_inliers(const uint16_t* labels, const float* xyz, int W, int H, int nLabels, const double* planes,
+                       int nPlanes, double threshold, uint32_t* inliers);
 /* depth: DepthModule (src/modules/depth.cpp:9-25): convertTo(CV_32F, 1/16) + cv::cuda::reprojectImageTo3D(Q), 3 channels */
 int orc_depth(const int16_t* disp, int W, int H, const float* Q16, float* xyz);
 int orc_find_peaks(const int32_t* hist, int n, int* out, int maxPeaks);

@@ -178,6 +178,70 @@ def sp_planeseg(deriv2, labels, max_label, hS, hE, vS, vE):
     return pu, ps
 
 
+def _ptr_array(arrs):
+    a = (C.c_void_p * max(1, len(arrs)))()
+    for i, x in enumerate(arrs):
+        a[i] = x.ctypes.data
+    return a
+
+
+def classify_temporal(deriv, hS, hE, vS, vE, prev_planes, prev_flow, channel_stride=1):
+    """prev_planes[k]: planes_unsmoothed of frame id-(k+1) (H, W) u8; prev_flow[k]: optflow of frame id-k (H, W, 2) int16 S10.5."""
+    deriv = _c(deriv, np.int16)
+    H, W = deriv.shape[:2]
+    pp = [_c(a, np.uint8) for a in prev_planes]
+    pf = [_c(a, np.int16) for a in prev_flow]
+    assert len(pp) == len(pf)
+    pu = np.empty((H, W), np.uint8)
+    ps = np.empty((H, W), np.uint8)
+    f = lib().orc_classify_temporal
+    f.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p] * 4
+    rc = f(_p(deriv), W, H, channel_stride, hS, hE, vS, vE, len(pp), _ptr_array(pp), _ptr_array(pf), _p(pu), _p(ps))
+    if rc != 0:
+        raise RuntimeError(f"orc_classify_temporal rc={rc}")
+    return pu, ps
+
+
+def sp_planeseg_temporal(deriv2, labels, max_label, hS, hE, vS, vE, prev_planes, prev_flow):
+    deriv2, labels = _c(deriv2, np.int16), _c(labels, np.uint16)
+    H, W = labels.shape
+    pp = [_c(a, np.uint8) for a in prev_planes]
+    pf = [_c(a, np.int16) for a in prev_flow]
+    assert len(pp) == len(pf)
+    pu = np.empty((H, W), np.uint8)
+    ps = np.empty((H, W), np.uint8)
+    f = lib().orc_sp_planeseg_temporal
+    f.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p] * 4
+    rc = f(_p(deriv2), _p(labels), W, H, max_label, hS, hE, vS, vE, len(pp), _ptr_array(pp), _ptr_array(pf), _p(pu), _p(ps))
+    if rc != 0:
+        raise RuntimeError(f"orc_sp_planeseg_temporal rc={rc}")
+    return pu, ps
+
+
+def label_statistics(labels, xyz, n_labels):
+    labels, xyz = _c(labels, np.uint16), _c(xyz, np.float32)
+    H, W = labels.shape
+    cnt = np.empty(n_labels, np.uint32)
+    inv = np.empty(n_labels, np.uint32)
+    rc = lib().orc_label_statistics(_p(labels), _p(xyz), W, H, n_labels, _p(cnt), _p(inv))
+    if rc != 0:
+        raise RuntimeError(f"orc_label_statistics rc={rc}")
+    return cnt, inv
+
+
+def region_inliers(labels, xyz, n_labels, planes, threshold):
+    labels, xyz = _c(labels, np.uint16), _c(xyz, np.float32)
+    planes = _c(np.asarray(planes, np.float64).reshape(-1, 4), np.float64)
+    H, W = labels.shape
+    out = np.empty((len(planes), n_labels), np.uint32)
+    f = lib().orc_region_inliers
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+    rc = f(_p(labels), _p(xyz), W, H, n_labels, _p(planes), len(planes), float(threshold), _p(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_region_inliers rc={rc}")
+    return out
+
+
 def find_peaks(hist):
     hist = _c(hist, np.int32)
     out = np.zeros((len(hist), 4), np.int32)

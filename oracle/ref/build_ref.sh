@@ -45,8 +45,11 @@ inc() { echo "#include \"$HERE/shim.h\""; }
   cut_ $SPI/features/compactness.cuh 28 58; cut_ $SP/features/compactness.cu 5 20; cut_ $SP/features/compactness.cu 28 197;
   echo "}"; cut_ $SP/contourrelaxation.cu 10 327; cat "$HERE/harness_contour.inc"; } > "$T/contour.cu"
 
+{ inc; cut_ $CU 10 15; cut_ $CU 31 36; echo "namespace cart {"; cut_ include/modules/planefit.hpp 18 23; echo "}";
+  cut_ src/modules/planefit.cu 14 138; cat "$HERE/harness_planefit.inc"; } > "$T/planefit.cu"
+
 FLAGS="-gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo --expt-relaxed-constexpr -Xcompiler -fPIC -w"
-for n in derivative naive sp_planeseg interpolate contour; do
+for n in derivative naive sp_planeseg interpolate contour planefit; do
   $NVCC $FLAGS -c "$T/$n.cu" -o "$T/$n.o"
 done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libref.so" "$T"/*.o -lcudart

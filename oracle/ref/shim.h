@@ -15,6 +15,9 @@
 #include <vector>
 
 namespace cv {
+struct Point3f {
+    float x, y, z;
+};
 namespace cuda {
 template <typename T>
 struct PtrStepSz {

@@ -17,6 +17,7 @@
 // vectors in tests/golden/ on the "defined" masks this file produces.
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -218,6 +219,131 @@ int orc_sp_planeseg(const int16_t* deriv2, const uint16_t* labels, int W, int H,
         assign[l] = best;
     }
     for (long i = 0; i < N; ++i) planes[i] = assign[labels[i]];
+    return 0;
+}
+
+// ---- temporal smoothing vote ---------------------------------------------------------
+// Per-pixel vote of classifyPlanes (planeseg.cu:199-240, mode 0) and of performSuperPixelClassifications
+// (sp_planeseg.cu:79-117, mode 1).  prevPlanes[k] = "planes_unsmoothed" of frame id-(k+1), prevFlow[k] = "optflow"
+// (CV_16SC2, S10.5) of frame id-k, both tightly packed here.  Every flow image is read at the CURRENT pixel, the
+// position walks back by the accumulated integer flow (arithmetic >> 5), positions outside the image are skipped
+// but stay accumulated.  Mode 0: current plane counts once, winner = H if votes[H] > votes[V] else V, UNKNOWN when
+// the winner has no vote.  Mode 1: current plane counts twice, UNKNOWN when it outvotes the winner.
+static inline uint8_t temporal_vote_px(int mode, uint8_t plane, int px, int py, int W, int H, int count,
+                                       const uint8_t* const* prevPlanes, const int16_t* const* prevFlow) {
+    int votes[3] = {0, 0, 0};
+    votes[plane] += mode ? 2 : 1;
+    int x = px, y = py;
+    for (int k = 0; k < count; ++k) {
+        const int16_t* fl = prevFlow[k] + ((size_t)py * W + px) * 2;
+        x -= (int16_t)fl[0] >> 5;
+        y -= (int16_t)fl[1] >> 5;
+        if (x < 0 || y < 0 || x >= W || y >= H) continue;
+        votes[prevPlanes[k][(size_t)y * W + x]]++;
+    }
+    int best = votes[0] > votes[1] ? 0 : 1;
+    if (mode == 0) {
+        if (votes[best] == 0) best = 2;
+    } else {
+        if (votes[best] < votes[2]) best = 2;
+    }
+    return (uint8_t)best;
+}
+
+// classifyPlanes with previousPlanesCount = count (planeseg.cu:160-243).  count == 0: the reference leaves the
+// smoothed image untouched and the module returns the unsmoothed image under both keys (planeseg.cu:361-368);
+// here smoothed = unsmoothed.  Returns -2 if a previous plane value is > 2 (the reference would index out of bounds).
+int orc_classify_temporal(const int16_t* deriv, int W, int H, int stride, int hS, int hE, int vS, int vE, int count,
+                          const uint8_t* const* prevPlanes, const int16_t* const* prevFlow, uint8_t* planesUnsmoothed,
+                          uint8_t* planesSmoothed) {
+    const long N = (long)W * H;
+    for (int k = 0; k < count; ++k)
+        for (long i = 0; i < N; ++i)
+            if (prevPlanes[k][i] > 2) return -2;
+    orc_classify(deriv, N, stride, hS, hE, vS, vE, planesUnsmoothed);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const size_t i = (size_t)y * W + x;
+            planesSmoothed[i] = count > 0 ? temporal_vote_px(0, planesUnsmoothed[i], x, y, W, H, count, prevPlanes, prevFlow)
+                                          : planesUnsmoothed[i];
+        }
+    return 0;
+}
+
+// performSuperPixelClassifications + classifyPlanes with previousPlanesCount = count (sp_planeseg.cu:25-184):
+// the per-pixel vote result (not the unsmoothed class) feeds the superpixel counters.
+int orc_sp_planeseg_temporal(const int16_t* deriv2, const uint16_t* labels, int W, int H, int maxLabel, int hS, int hE,
+                             int vS, int vE, int count, const uint8_t* const* prevPlanes, const int16_t* const* prevFlow,
+                             uint8_t* planesUnsmoothed, uint8_t* planes) {
+    if ((size_t)(maxLabel + 1) * 3 * sizeof(uint16_t) > 32768) return -3;
+    const long N = (long)W * H;
+    for (int k = 0; k < count; ++k)
+        for (long i = 0; i < N; ++i)
+            if (prevPlanes[k][i] > 2) return -2;
+    orc_classify(deriv2, N, 2, hS, hE, vS, vE, planesUnsmoothed);
+    std::vector<uint32_t> votes((size_t)maxLabel * 3, 0);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const size_t i = (size_t)y * W + x;
+            if (labels[i] >= maxLabel) return -2;
+            const uint8_t p = count > 0 ? temporal_vote_px(1, planesUnsmoothed[i], x, y, W, H, count, prevPlanes, prevFlow)
+                                        : planesUnsmoothed[i];
+            if (++votes[(size_t)labels[i] * 3 + p] > 65535u) return -4;
+        }
+    for (long i = 0; i < N; ++i) {
+        const uint32_t* v = &votes[(size_t)labels[i] * 3];
+        int maxVotes = (int)v[2];
+        uint8_t best = 2;
+        if ((int)v[1] > maxVotes) {
+            maxVotes = (int)v[1];
+            best = 1;
+        }
+        if ((int)v[0] > maxVotes) best = 0;
+        planes[i] = best;
+    }
+    return 0;
+}
+
+// ---- superpixel consumers of the plane fit ---------------------------------------------
+// IS_VALID_DEPTH, planefit.cu:19: finite, <= 40 and > 0 (float compared against double constants).
+static inline bool valid_depth(float z) { return std::isfinite(z) && (double)z <= 40.0 && (double)z > 0.0; }
+
+// countPixels, planefit.cu:38-83: per label the pixel count and the count of pixels whose depth Z is invalid.
+// The reference keeps both in uint16 counters updated with a non-carry-safe 16-bit atomic (cuda.cuh:31-36);
+// this restatement counts in 32 bits and returns -4 when a count would not fit 16 bits (the reference's result is
+// then corrupted by the carry into the neighbouring counter).  labels < nLabels (= maxLabelId + 1) or -2.
+int orc_label_statistics(const uint16_t* labels, const float* xyz, int W, int H, int nLabels, uint32_t* pixelCount,
+                         uint32_t* pixelCountInvalid) {
+    for (int l = 0; l < nLabels; ++l) pixelCount[l] = pixelCountInvalid[l] = 0;
+    for (long i = 0; i < (long)W * H; ++i) {
+        const int l = labels[i];
+        if (l >= nLabels) return -2;
+        if (!valid_depth(xyz[3 * i + 2])) pixelCountInvalid[l]++;
+        pixelCount[l]++;
+    }
+    for (int l = 0; l < nLabels; ++l)
+        if (pixelCount[l] > 65535u) return -4;
+    return 0;
+}
+
+// calculateRegionDistance, planefit.cu:85-138 with calculateDistanceFromPlane :34-36: inliers[plane][label] = number
+// of valid-depth pixels of the label closer than `threshold` to plane (a, b, c, d); double arithmetic on float
+// coordinates, evaluated left to right without contraction.  planes: nPlanes x 4 doubles.
+int orc_region_inliers(const uint16_t* labels, const float* xyz, int W, int H, int nLabels, const double* planes,
+                       int nPlanes, double threshold, uint32_t* inliers) {
+    for (long i = 0; i < (long)nPlanes * nLabels; ++i) inliers[i] = 0;
+    for (int p = 0; p < nPlanes; ++p) {
+        const double a = planes[4 * p], b = planes[4 * p + 1], c = planes[4 * p + 2], d = planes[4 * p + 3];
+        const double norm = std::sqrt(a * a + b * b + c * c);
+        for (long i = 0; i < (long)W * H; ++i) {
+            const int l = labels[i];
+            if (l >= nLabels) return -2;
+            const float* q = xyz + 3 * i;
+            if (!valid_depth(q[2])) continue;
+            const double dist = std::fabs(a * (double)q[0] + b * (double)q[1] + c * (double)q[2] + d) / norm;
+            if (dist < threshold) inliers[(size_t)p * nLabels + l]++;
+        }
+    }
     return 0;
 }
 

@@ -131,3 +131,56 @@ def test_depth_module_through_the_json_pipeline():
         o = po.depth(out["disparity"][i], Q)
         fin = np.isfinite(o)
         assert np.allclose(out["depth"][i][fin], o[fin], rtol=1e-6, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sequential", [True, False])
+def test_temporal_smoothing_through_the_json_pipeline(sequential):
+    """use_temporal_smoothing with an externally supplied flow ("external_optflow" stands in for the
+    NVOFA module), naive and superpixel planeseg, against the oracle's restatement of the module logic."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import ref_pipeline as rp
+
+    W, H, D, n = 160, 64, 64, 9
+    L, R, fr = _frames(W, H, D, n, tint=True)
+    flow = {i + 1: rp.constant_flow(H, W, 3.0, -0.5) for i in range(n)}
+    static = {"type": "static", "horizontal_range_min": 1, "horizontal_range_max": 30, "vertical_range_min": -3,
+              "vertical_range_max": 1}
+    cfg = dict(D=D, radius=2, iters=1)
+    # naive planeseg, distance 2
+    modules = [
+        {"type": "external_optflow", "flow_x": 3.0, "flow_y": -0.5},
+        {"type": "disparity", "num_disparities": D, "smoothing_radius": 2, "smoothing_iterations": 1},
+        {"type": "disparity_planeseg", "parameter_provider": static, "use_temporal_smoothing": True, "temporal_smoothing_distance": 2},
+    ]
+    out = host.run_config(modules, L, R, sequential=sequential, want_disparity=True)
+    ref = rp.naive_sequence(fr, cfg, provider="static", static=(1, 30, -3, 1), temporal=dict(distance=2, flow=flow))
+    for i in range(n):
+        assert np.array_equal(out["disparity"][i], ref[i]["disparity"]), i
+        assert np.array_equal(out["planes"][i], ref[i]["planes"]), i
+    assert any((ref[i]["planes"] != ref[i]["unsm"]).any() for i in range(1, n))
+    # superpixel planeseg, default distance 3 (kitti-planeseg.json shape)
+    modules = [
+        {"type": "superpixels", "initial_iterations": 5, "iterations": 2, "block_size": 8, "reset_iterations": 8},
+        {"type": "external_optflow", "flow_x": 3.0, "flow_y": -0.5},
+        {"type": "disparity", "num_disparities": D, "smoothing_radius": 2, "smoothing_iterations": 1},
+        {"type": "disparity_derivative"},
+        {"type": "superpixel_disparity_planeseg", "parameter_provider": static, "use_temporal_smoothing": True},
+    ]
+    out = host.run_config(modules, L, R, sequential=sequential, want_labels=True)
+    ref = rp.sp_sequence(fr, cfg, provider="static", static=(1, 30, -3, 1), initial=5, steady=2, sp_reset=8, block=8,
+                         temporal=dict(distance=3, flow=flow))
+    for i in range(n):
+        assert np.array_equal(out["labels"][i], ref[i]["labels"]), i
+        assert np.array_equal(out["planes"][i], ref[i]["planes"]), i
+
+
+def test_temporal_smoothing_needs_a_flow_provider_and_a_sane_distance():
+    L = np.zeros((1, 32, 64, 3), np.uint8)
+    static = {"type": "static", "horizontal_range_min": 1, "horizontal_range_max": 30, "vertical_range_min": -3,
+              "vertical_range_max": 1}
+    with pytest.raises(host.HostError, match="temporal_smoothing_distance"):
+        host.run_config([{"type": "external_optflow"}, {"type": "disparity_planeseg", "parameter_provider": static,
+                                                        "use_temporal_smoothing": True, "temporal_smoothing_distance": 9}], L, L)
