@@ -100,6 +100,8 @@ def _load():
     lib.cartb200_histogram_peak_update.argtypes = [vp, vp]
     lib.cartb200_classify_temporal.argtypes = [vp, vp, sz, i, i, vp, i, vp, vp, vp, sz, vp]
     lib.cartb200_sp_planeseg_temporal.argtypes = [vp, vp, sz, vp, sz, i, vp, i, vp, vp, vp, sz, vp]
+    lib.cartb200_overlay_planes.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp]
+    lib.cartb200_overlay_superpixel_boundaries.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp]
     lib.cartb200_label_statistics.argtypes = [vp, vp, sz, vp, sz, i, vp, vp, vp]
     lib.cartb200_region_inliers.argtypes = [vp, vp, sz, vp, sz, i, vp, i, C.c_double, vp, vp]
     lib.cartb200_run_sequence_host.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp, vp]
@@ -456,6 +458,25 @@ class Context:
         out = torch.empty((pl.shape[0], n_labels), dtype=torch.int32, device=labels.device)
         self._check(_lib.cartb200_region_inliers(self._h, lp, lpitch, xp, xpitch, n_labels, pl.ctypes.data, pl.shape[0],
                                                  float(threshold), out.data_ptr(), self._stream()))
+        return out
+
+    def overlay_planes(self, image_bgr, planes):
+        """overlayPlanes: image [H,W,3] u8 + planes [H,W] u8 -> blended BGR image."""
+        torch = self.torch
+        _, ip, ipitch, _ = self._img(image_bgr[None], torch.uint8, 3)
+        _, pp, ppitch, _ = self._img(planes[None], torch.uint8)
+        out = torch.empty_like(image_bgr)
+        self._check(_lib.cartb200_overlay_planes(self._h, ip, ipitch, pp, ppitch, out.data_ptr(), self.W * 3, self._stream()))
+        return out
+
+    def overlay_superpixel_boundaries(self, image_bgr, labels, out=None):
+        """overlayBoundaryVisualization; `out` keeps its last row / column (zeros when not given)."""
+        torch = self.torch
+        _, ip, ipitch, _ = self._img(image_bgr[None], torch.uint8, 3)
+        _, lp, lpitch, _ = self._img(labels[None], torch.uint16)
+        out = torch.zeros_like(image_bgr) if out is None else out
+        self._check(_lib.cartb200_overlay_superpixel_boundaries(self._h, ip, ipitch, lp, lpitch, out.data_ptr(), self.W * 3,
+                                                                self._stream()))
         return out
 
     # -- superpixels -----------------------------------------------------------------------------

@@ -601,6 +601,27 @@ int cartb200_region_inliers(cartb200_ctx* c, const uint16_t* labels, size_t lp, 
                                  threshold, inliers, (cudaStream_t)stream);
 }
 
+int cartb200_overlay_planes(cartb200_ctx* c, const uint8_t* bgr, size_t bp, const uint8_t* planes, size_t pp, uint8_t* out, size_t op,
+                            void* stream) {
+    if (!c) return CARTB200_E_ARG;
+    if (!bgr || !planes || !out || bp < (size_t)c->W * 3 || pp < (size_t)c->W || op < (size_t)c->W * 3) {
+        c->err = "overlay_planes: bad arguments";
+        return CARTB200_E_ARG;
+    }
+    return launch_overlay_planes(c, Img<const uint8_t>{bgr, bp}, Img<const uint8_t>{planes, pp}, Img<uint8_t>{out, op}, (cudaStream_t)stream);
+}
+
+int cartb200_overlay_superpixel_boundaries(cartb200_ctx* c, const uint8_t* bgr, size_t bp, const uint16_t* labels, size_t lp, uint8_t* out,
+                                           size_t op, void* stream) {
+    if (!c) return CARTB200_E_ARG;
+    if (!bgr || !labels || !out || bp < (size_t)c->W * 3 || lp < (size_t)c->W * 2 || op < (size_t)c->W * 3) {
+        c->err = "overlay_superpixel_boundaries: bad arguments";
+        return CARTB200_E_ARG;
+    }
+    return launch_overlay_boundaries(c, Img<const uint8_t>{bgr, bp}, Img<const uint16_t>{labels, lp}, Img<uint8_t>{out, op},
+                                     (cudaStream_t)stream);
+}
+
 int cartb200_depth(cartb200_ctx* c, int n, const int16_t* d, size_t dp, size_t dfs, const float* q16Host, float* xyz, size_t xp,
                    size_t xfs, void* stream) {
     int rc = checkBatch(c, n);

@@ -144,6 +144,8 @@ int launch_classify_temporal(cartb200_ctx* c, Img<const int16_t> deriv, int chan
 int launch_sp_planeseg_temporal(cartb200_ctx* c, Img<const int16_t> deriv, Img<const uint16_t> labels, int maxLabel, PlaneRanges pr, const TemporalRefs& refs, Img<uint8_t> unsm, Img<uint8_t> planes, cudaStream_t s);
 int launch_label_statistics(cartb200_ctx* c, Img<const uint16_t> labels, Img<const float> xyz, int nLabels, uint32_t* count, uint32_t* invalid, cudaStream_t s);
 int launch_region_inliers(cartb200_ctx* c, Img<const uint16_t> labels, Img<const float> xyz, int nLabels, const double* planesHost, int nPlanes, double threshold, uint32_t* inliers, cudaStream_t s);
+int launch_overlay_planes(cartb200_ctx* c, Img<const uint8_t> bgr, Img<const uint8_t> planes, Img<uint8_t> out, cudaStream_t s);
+int launch_overlay_boundaries(cartb200_ctx* c, Img<const uint8_t> bgr, Img<const uint16_t> labels, Img<uint8_t> out, cudaStream_t s);
 int launch_depth(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<float> xyz, const float* q16Host, cudaStream_t s);
 int launch_border_map(cartb200_ctx* c, Img<const uint16_t> labels, Img<uint8_t> border, cudaStream_t s);
 void build_sp_tile_tables(int W, int H, std::vector<int>& tileMap, std::vector<uint32_t>& tab);

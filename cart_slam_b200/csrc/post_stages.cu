@@ -482,6 +482,50 @@ int launch_region_inliers(cartb200_ctx* c, Img<const uint16_t> labels, Img<const
 }
 
 // ---------------------------------------------------------------------------------------------
+// Overlay kernels (visual QA).  overlayPlanes, /root/reference/src/modules/planeseg/planeseg_vis.cu:28-56
+// (colour table :21-26 = PlaneColor / 2, /root/reference/include/modules/planeseg.hpp:44-66) and
+// overlayBoundaryVisualization, /root/reference/src/modules/superpixels/visualization.cu:9-42 (last row / column not
+// written).  One thread per pixel, 7 B of traffic per pixel: HBM-bound, launch-latency sized at one frame.
+__global__ void __launch_bounds__(256) overlay_planes_kernel(Img<const uint8_t> bgr, Img<const uint8_t> planes, Img<uint8_t> out, int W,
+                                                             int H) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const unsigned p = __ldg(planes.row(y) + x);
+    const uint8_t* in = bgr.row(y) + 3 * (size_t)x;
+    uint8_t* o = out.row(y) + 3 * (size_t)x;
+    o[0] = (uint8_t)(__ldg(in) / 2 + (p == CARTB200_PLANE_HORIZONTAL ? 127 : 0));
+    o[1] = (uint8_t)(__ldg(in + 1) / 2 + (p == CARTB200_PLANE_VERTICAL ? 127 : 0));
+    o[2] = (uint8_t)(__ldg(in + 2) / 2 + (p == CARTB200_PLANE_UNKNOWN ? 127 : 0));
+}
+
+__global__ void __launch_bounds__(256) overlay_boundaries_kernel(Img<const uint8_t> bgr, Img<const uint16_t> labels, Img<uint8_t> out,
+                                                                 int W, int H) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W - 1 || y >= H - 1) return;
+    const unsigned l = __ldg(labels.row(y) + x);
+    const bool edge = l != __ldg(labels.row(y) + x + 1) || l != __ldg(labels.row(y + 1) + x);
+    const uint8_t* in = bgr.row(y) + 3 * (size_t)x;
+    uint8_t* o = out.row(y) + 3 * (size_t)x;
+    o[0] = edge ? 0 : __ldg(in);
+    o[1] = edge ? 0 : __ldg(in + 1);
+    o[2] = edge ? 255 : __ldg(in + 2);
+}
+
+int launch_overlay_planes(cartb200_ctx* c, Img<const uint8_t> bgr, Img<const uint8_t> planes, Img<uint8_t> out, cudaStream_t s) {
+    dim3 grid(ceilDiv(c->W, 256), c->H, 1);
+    overlay_planes_kernel<<<grid, 256, 0, s>>>(bgr, planes, out, c->W, c->H);
+    CB_LAUNCH_CHECK(c);
+    return CARTB200_OK;
+}
+
+int launch_overlay_boundaries(cartb200_ctx* c, Img<const uint8_t> bgr, Img<const uint16_t> labels, Img<uint8_t> out, cudaStream_t s) {
+    dim3 grid(ceilDiv(c->W, 256), c->H, 1);
+    overlay_boundaries_kernel<<<grid, 256, 0, s>>>(bgr, labels, out, c->W, c->H);
+    CB_LAUNCH_CHECK(c);
+    return CARTB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // DepthModule::runInternal, /root/reference/src/modules/depth.cpp:9-25: disparity * (1/16) as float, then the
 // third-party cv::cuda::reprojectImageTo3D(Q, 3 channels).  Normative arithmetic: oracle/stages.cpp orc_depth
 // (single precision, same operation order; compiled without FMA contraction).  12 B written per pixel: HBM-bound.

@@ -220,6 +220,18 @@ int cartb200_region_inliers(cartb200_ctx* ctx, const uint16_t* labels, size_t la
                             size_t depth_pitch, int n_labels, const double* planes_host, int n_planes, double threshold,
                             uint32_t* inliers, void* stream);
 
+/* Overlay kernels of the same row (visual QA).  overlay_planes replaces overlayPlanes
+ * (/root/reference/src/modules/planeseg/planeseg_vis.cu:28-56): out = image / 2 + PlaneColor[plane] / 2 (BGR, CV_8UC3).
+ * overlay_superpixel_boundaries replaces overlayBoundaryVisualization
+ * (/root/reference/src/modules/superpixels/visualization.cu:9-42, called from computeBoundaryOverlay :46-66): pixels whose
+ * right or lower neighbour has another label turn red; the last row and column of `out` are not written, as in the
+ * reference. */
+int cartb200_overlay_planes(cartb200_ctx* ctx, const uint8_t* image_bgr, size_t image_pitch, const uint8_t* planes,
+                            size_t planes_pitch, uint8_t* out_bgr, size_t out_pitch, void* stream);
+int cartb200_overlay_superpixel_boundaries(cartb200_ctx* ctx, const uint8_t* image_bgr, size_t image_pitch,
+                                           const uint16_t* labels, size_t labels_pitch, uint8_t* out_bgr, size_t out_pitch,
+                                           void* stream);
+
 /* ---- depth (the stage right after disparity) ------------------------------
  * Replaces DepthModule::runInternal (/root/reference/src/modules/depth.cpp:9-25): convertTo(CV_32F, 1/16) +
  * cv::cuda::reprojectImageTo3D(disparityFloat, depth, Q, 3).  q16_host: the 4x4 reprojection matrix Q

@@ -41,6 +41,9 @@ int orc_label_statistics(const uint16_t* labels, const float* xyz, int W, int H,
                          uint32_t* pixelCountInvalid);
 int orc_region_inliers(const uint16_t* labels, const float* xyz, int W, int H, int nLabels, const double* planes,
                        int nPlanes, double threshold, uint32_t* inliers);
+/* overlay kernels: overlayPlanes (planeseg_vis.cu:28-56), overlayBoundaryVisualization (superpixels/visualization.cu:9-42) */
+int orc_overlay_planes(const uint8_t* bgr, const uint8_t* planes, int W, int H, uint8_t* out);
+int orc_overlay_boundaries(const uint8_t* bgr, const uint16_t* labels, int W, int H, uint8_t* out);
 /* depth: DepthModule (src/modules/depth.cpp:9-25): convertTo(CV_32F, 1/16) + cv::cuda::reprojectImageTo3D(Q), 3 channels */
 int orc_depth(const int16_t* disp, int W, int H, const float* Q16, float* xyz);
 int orc_find_peaks(const int32_t* hist, int n, int* out, int maxPeaks);

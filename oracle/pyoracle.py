@@ -242,6 +242,25 @@ def region_inliers(labels, xyz, n_labels, planes, threshold):
     return out
 
 
+def overlay_planes(bgr, planes):
+    bgr, planes = _c(bgr, np.uint8), _c(planes, np.uint8)
+    H, W = planes.shape
+    out = np.empty((H, W, 3), np.uint8)
+    rc = lib().orc_overlay_planes(_p(bgr), _p(planes), W, H, _p(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_overlay_planes rc={rc}")
+    return out
+
+
+def overlay_boundaries(bgr, labels, out=None):
+    """`out` (H, W, 3) keeps its last row and column, like the reference's output image."""
+    bgr, labels = _c(bgr, np.uint8), _c(labels, np.uint16)
+    H, W = labels.shape
+    out = np.zeros((H, W, 3), np.uint8) if out is None else _c(out, np.uint8).copy()
+    lib().orc_overlay_boundaries(_p(bgr), _p(labels), W, H, _p(out))
+    return out
+
+
 def find_peaks(hist):
     hist = _c(hist, np.int32)
     out = np.zeros((len(hist), 4), np.int32)

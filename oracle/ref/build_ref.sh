@@ -48,8 +48,13 @@ inc() { echo "#include \"$HERE/shim.h\""; }
 { inc; cut_ $CU 10 15; cut_ $CU 31 36; echo "namespace cart {"; cut_ include/modules/planefit.hpp 18 23; echo "}";
   cut_ src/modules/planefit.cu 14 138; cat "$HERE/harness_planefit.inc"; } > "$T/planefit.cu"
 
+{ inc; cut_ $CU 10 15; echo "namespace cart {"; cut_ include/modules/planeseg.hpp 36 66; echo "}";
+  cut_ src/modules/planeseg/planeseg_vis.cu 14 56; cat "$HERE/harness_overlay.inc"; } > "$T/overlay.cu"
+
+{ inc; cut_ $CU 10 15; cut_ src/modules/superpixels/visualization.cu 4 42; cat "$HERE/harness_overlay_sp.inc"; } > "$T/overlay_sp.cu"
+
 FLAGS="-gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo --expt-relaxed-constexpr -Xcompiler -fPIC -w"
-for n in derivative naive sp_planeseg interpolate contour planefit; do
+for n in derivative naive sp_planeseg interpolate contour planefit overlay overlay_sp; do
   $NVCC $FLAGS -c "$T/$n.cu" -o "$T/$n.o"
 done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libref.so" "$T"/*.o -lcudart

@@ -347,6 +347,33 @@ int orc_region_inliers(const uint16_t* labels, const float* xyz, int W, int H, i
     return 0;
 }
 
+// ---- overlay kernels (visual QA) -------------------------------------------------------------
+// overlayPlanes, planeseg_vis.cu:28-56 with the colour table :21-26 (PlaneColor, planeseg.hpp:44-66, halved):
+// out = bgr / 2 + colour[plane] / 2 per channel.  Plane values > 2 index past the table in the reference: -2 here.
+int orc_overlay_planes(const uint8_t* bgr, const uint8_t* planes, int W, int H, uint8_t* out) {
+    static const int colors[3][3] = {{255 / 2, 0, 0}, {0, 255 / 2, 0}, {0, 0, 255 / 2}};  // B, G, R of H / V / UNKNOWN
+    for (long i = 0; i < (long)W * H; ++i) {
+        if (planes[i] > 2) return -2;
+        for (int c = 0; c < 3; ++c) out[3 * i + c] = (uint8_t)(bgr[3 * i + c] / 2 + colors[planes[i]][c]);
+    }
+    return 0;
+}
+
+// overlayBoundaryVisualization, superpixels/visualization.cu:9-42: a pixel whose right or lower neighbour carries a
+// different label becomes red (0, 0, 255), the others copy the image; the last row and the last column are NOT
+// written (:20-22) - `out` keeps whatever it held there.
+int orc_overlay_boundaries(const uint8_t* bgr, const uint16_t* labels, int W, int H, uint8_t* out) {
+    for (int y = 0; y < H - 1; ++y)
+        for (int x = 0; x < W - 1; ++x) {
+            const size_t i = (size_t)y * W + x;
+            const bool edge = labels[i] != labels[i + 1] || labels[i] != labels[i + W];
+            out[3 * i] = edge ? 0 : bgr[3 * i];
+            out[3 * i + 1] = edge ? 0 : bgr[3 * i + 1];
+            out[3 * i + 2] = edge ? 255 : bgr[3 * i + 2];
+        }
+    return 0;
+}
+
 // ---- host-side parameter estimation --------------------------------------------------------------
 
 struct Peak {

@@ -54,6 +54,14 @@ def main():
         inl = np.zeros((len(d["planes"]), d["n_labels"]), np.uint32)
         assert f(p(d["labels"]), p(d["xyz"]), W, H, d["n_labels"], p(d["planes"]), len(d["planes"]), thr, p(inl)) == 0
         out[f"inliers_{i}"] = inl
+    # overlay kernels (visual QA): plane overlay on the reference's own superpixel planes, boundary overlay on its labels
+    bgr = np.ascontiguousarray(base["left_bgr"])
+    ov = np.zeros((H, W, 3), np.uint8)
+    assert lib.ref_overlay_planes(p(bgr), p(np.ascontiguousarray(base["sp_planes"])), W, H, p(ov)) == 0
+    out["overlay_planes"] = ov
+    ob = np.full((H, W, 3), 77, np.uint8)
+    assert lib.ref_overlay_boundaries(p(bgr), p(d["labels"]), W, H, p(ob)) == 0
+    out["overlay_boundaries"] = ob
     np.savez_compressed(os.path.join(HERE, "ref_kernels_f34.npz"), **out)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     np.savez_compressed(os.path.join(ROOT, "gpurun_out", "ref_kernels_f34.npz"), **out)

@@ -161,6 +161,29 @@ def test_golden_planefit_consumers(inp, gold):
         assert np.abs(got.astype(np.int64) - ref.astype(np.int64)).sum() <= 2, i
 
 
+def test_oracle_overlays_and_golden(inp):
+    base = np.load(BASE)
+    bgr, planes, labels = base["left_bgr"], base["sp_planes"], inp["labels"]
+    ov = po.overlay_planes(bgr, planes)
+    col = np.zeros(planes.shape + (3,), np.int32)
+    for pl in range(3):
+        col[..., pl][planes == pl] = 127  # H -> blue, V -> green, UNKNOWN -> red (BGR order)
+    assert np.array_equal(ov, (bgr // 2 + col).astype(np.uint8))
+    ob = po.overlay_boundaries(bgr, labels, out=np.full(bgr.shape, 77, np.uint8))
+    edge = np.zeros(labels.shape, bool)
+    edge[:-1, :-1] = (labels[:-1, :-1] != labels[:-1, 1:]) | (labels[:-1, :-1] != labels[1:, :-1])
+    exp = bgr.copy()
+    exp[edge] = (0, 0, 255)
+    exp[-1, :] = 77
+    exp[:, -1] = 77
+    assert np.array_equal(ob, exp)
+    with pytest.raises(RuntimeError):
+        po.overlay_planes(bgr, np.full(planes.shape, 3, np.uint8))
+    if os.path.exists(GOLD) and "overlay_planes" in np.load(GOLD).files:  # the reference's own kernels
+        g = np.load(GOLD)
+        assert np.array_equal(ov, g["overlay_planes"]) and np.array_equal(ob, g["overlay_boundaries"])
+
+
 # ---- CUDA path through the C ABI --------------------------------------------------------------------------------
 def _ctx(W, H, superpixels=True, block=12):
     import cart_slam_b200 as cb
@@ -235,3 +258,19 @@ def test_gpu_planefit_consumers_bit_exact(inp):
         for thr in inp["thresholds"]:
             got = ctx.region_inliers(dev(inp["labels"]), dev(inp["xyz"]), n, planes, thr).cpu().numpy().astype(np.uint32)
             assert np.array_equal(got, po.region_inliers(inp["labels"], inp["xyz"], n, planes, thr))
+
+
+@pytest.mark.gpu
+def test_gpu_overlays_bit_exact(inp):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    base = np.load(BASE)
+    bgr, planes, labels = base["left_bgr"], base["sp_planes"], inp["labels"]
+    H, W = labels.shape
+    with _ctx(W, H, superpixels=False) as ctx:
+        assert np.array_equal(ctx.overlay_planes(dev(bgr), dev(planes)).cpu().numpy(), po.overlay_planes(bgr, planes))
+        seed = np.full(bgr.shape, 77, np.uint8)
+        got = ctx.overlay_superpixel_boundaries(dev(bgr), dev(labels), out=dev(seed)).cpu().numpy()
+        assert np.array_equal(got, po.overlay_boundaries(bgr, labels, out=seed))
