@@ -100,6 +100,7 @@ struct PathArgs {
     size_t volFrameStride;
     int W, H, P1, P2;
     int dx, dy;
+    uint32_t P1v, P2v, negP1v;  // (P1, P1), (P2, P2), (-P1, -P1) mod 2^16 as u16x2: read straight from the constant bank
 };
 
 __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return hi * 65536u + lo; }
@@ -141,6 +142,87 @@ __device__ __forceinline__ uint32_t dp_step(uint32_t (&dp)[8], const uint32_t (&
     mn = __vimin3_u16x2(mn, dp[5], dp[6]);
     mn = __vminu2(mn, dp[7]);
     return min(mn & 0xFFFFu, mn >> 16);
+}
+
+// Leaner formulation used by the axis-aligned kernels.
+//  * Register i of a lane holds the pair (d_i, d_{i+8}) of its 16 disparities, so the d-1 / d+1 neighbours of register
+//    i are simply registers i-1 / i+1; only the two ends need a PRMT with the adjacent lane's value (2 instead of 9).
+//  * The state carried between pixels is K = (P1 - m, P1 - m) (one true 32-bit value, halves independent): qp = dp + K
+//    is the P1-penalised neighbour value and, through qc = min(qp - P1, P2) with the constant (-P1, -P1), the centre
+//    term - no per-pixel negation of m.
+//  * The end-of-range sentinels are OR-masks computed once per thread; the lane minimum is returned replicated in both
+//    halves so the group reduction stays packed and its result is (m, m), the next K's subtrahend.
+constexpr uint32_t kSentinelHi = 0x7FFF0000u, kSentinelLo = 0x00007FFFu;
+
+template <int LPP>
+__device__ __forceinline__ uint32_t dp_step2(uint32_t (&dp)[8], const uint32_t (&cost)[16], uint32_t K, uint32_t maskUp,
+                                             uint32_t maskDn, uint32_t negP1v, uint32_t P2v) {
+    uint32_t qp[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qp[i] = dp[i] + K;
+    // previous lane's (d7, d15): its d15 is this lane's d-1 neighbour of d0; next lane's (d0, d8): its d0 follows d15
+    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, qp[7], 1) | maskUp;    // maskUp = kSentinelHi on the first lane
+    const uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, qp[0], 1) | maskDn;  // maskDn = kSentinelLo on the last lane
+    const uint32_t lower0 = __byte_perm(up, qp[7], 0x5432);  // (d-1, d7): lower neighbours of register 0 = (d0, d8)
+    const uint32_t upper7 = __byte_perm(qp[0], dn, 0x5432);  // (d8, d16): upper neighbours of register 7 = (d7, d15)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t qc = __viaddmin_u16x2(qp[i], negP1v, P2v);
+        dp[i] = __vimin3_u16x2(i == 0 ? lower0 : qp[i - 1], i == 7 ? upper7 : qp[i + 1], qc) + cost[i] + (cost[i + 8] << 16);
+    }
+    uint32_t mn = __vimin3_u16x2(dp[0], dp[1], dp[2]);
+    mn = __vimin3_u16x2(mn, dp[3], dp[4]);
+    mn = __vimin3_u16x2(mn, dp[5], dp[6]);
+    mn = __vminu2(mn, dp[7]);
+    return __vminu2(mn, __byte_perm(mn, 0, 0x1032));  // (min, min)
+}
+
+// registers (d_i, d_{i+8}) -> 16 bytes d0 .. d15
+__device__ __forceinline__ void store_dp2(uint8_t* dst, const uint32_t (&dp)[8]) {
+    const uint32_t A = __byte_perm(dp[0], dp[1], 0x6420);  // d0 d8 d1 d9
+    const uint32_t B = __byte_perm(dp[2], dp[3], 0x6420);  // d2 d10 d3 d11
+    const uint32_t C = __byte_perm(dp[4], dp[5], 0x6420);
+    const uint32_t E = __byte_perm(dp[6], dp[7], 0x6420);
+    uint4 o;
+    o.x = __byte_perm(A, B, 0x6420);
+    o.y = __byte_perm(C, E, 0x6420);
+    o.z = __byte_perm(A, B, 0x7531);
+    o.w = __byte_perm(C, E, 0x7531);
+    __stcs(reinterpret_cast<uint4*>(dst), o);  // streaming store: the volume is not re-read before the WTA pass
+}
+
+// The same step with registers in natural order (d_2i, d_2i+1): 9 neighbour PRMTs, 4 for the store.  The vertical kernel
+// keeps this one (measured: the interleaved step raises it from 80 to 96 registers and costs it a resident CTA).
+template <int LPP>
+__device__ __forceinline__ uint32_t dp_step2n(uint32_t (&dp)[8], const uint32_t (&cost)[16], uint32_t K, uint32_t maskUp,
+                                              uint32_t maskDn, uint32_t negP1v, uint32_t P2v) {
+    uint32_t qp[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qp[i] = dp[i] + K;
+    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, qp[7], 1) | maskUp;    // maskUp / maskDn = kSentinel2 at the range ends
+    const uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, qp[0], 1) | maskDn;
+    uint32_t sp[9];
+    sp[0] = __byte_perm(up, qp[0], 0x5432);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) sp[i] = __byte_perm(qp[i - 1], qp[i], 0x5432);
+    sp[8] = __byte_perm(qp[7], dn, 0x5432);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t qc = __viaddmin_u16x2(qp[i], negP1v, P2v);
+        dp[i] = __vimin3_u16x2(sp[i], sp[i + 1], qc) + cost[2 * i] + (cost[2 * i + 1] << 16);
+    }
+    uint32_t mn = __vimin3_u16x2(dp[0], dp[1], dp[2]);
+    mn = __vimin3_u16x2(mn, dp[3], dp[4]);
+    mn = __vimin3_u16x2(mn, dp[5], dp[6]);
+    mn = __vminu2(mn, dp[7]);
+    return __vminu2(mn, __byte_perm(mn, 0, 0x1032));  // (min, min)
+}
+
+template <int LPP>
+__device__ __forceinline__ uint32_t group_min2(uint32_t v) {  // packed u16x2 minimum over the group's lanes
+#pragma unroll
+    for (int o = 1; o < LPP; o <<= 1) v = __vminu2(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
 }
 
 template <int LPP>
@@ -190,13 +272,18 @@ __device__ __forceinline__ void horizontal_body(const PathArgs& a, uint8_t* __re
     const uint32_t* cl = a.cenL + (size_t)f * a.cenFrameStride + (size_t)y * a.cenStride + a.cenMargin;
     const uint32_t* cr = a.cenR + (size_t)f * a.cenFrameStride + (size_t)y * a.cenStride + a.cenMargin - 16 * lane - 16;
     uint8_t* vrow = volBase + (size_t)f * a.volFrameStride + (size_t)y * W * D + 16 * lane;
-    const uint32_t P1v = pack16(a.P1, a.P1), P2v = pack16(a.P2, a.P2);
+    const uint32_t maskUp = lane == 0 ? kSentinelHi : 0u, maskDn = lane == LPP - 1 ? kSentinelLo : 0u;
     const int nChunks = (W + U - 1) / U;
+    // keep the three packed constants in registers (the compiler otherwise re-reads them from the constant bank per pixel)
+    uint32_t P1v, P2v, negP1v;
+    asm volatile("mov.u32 %0, %1;" : "=r"(P1v) : "r"(a.P1v));
+    asm volatile("mov.u32 %0, %1;" : "=r"(P2v) : "r"(a.P2v));
+    asm volatile("mov.u32 %0, %1;" : "=r"(negP1v) : "r"(a.negP1v));
 
     uint32_t dp[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dp[i] = 0;
-    uint32_t m = 0;
+    uint32_t K = P1v;  // m = 0
     // S[k] = shifted right census word (x0 - 16*lane - 16 + k) of the current U-pixel chunk starting at x0
     uint32_t S[16 + U];
     uint32_t Lw[U], Ln[U], Sn[U];  // current chunk's left words; next chunk's left / right words (prefetched)
@@ -224,16 +311,23 @@ __device__ __forceinline__ void horizontal_body(const PathArgs& a, uint8_t* __re
             load_words<U>(Lw, cl + x0);
             load_words<U>(DX > 0 ? S + 16 : S, cr + x0 + (DX > 0 ? 16 : 0));
         }
+        uint8_t* vchunk = vrow + (size_t)x0 * D;  // stores of the chunk use immediate offsets from here
+        auto step = [&](int sidx) {
+            uint32_t cost[16];
 #pragma unroll
-        for (int t = 0; t < U; ++t) {
-            const int sidx = DX > 0 ? t : U - 1 - t;
-            const int x = x0 + sidx;
-            if (x < W) {  // warp-uniform: every group of the warp is at the same column
-                uint32_t cost[16];
+            for (int k = 0; k < 16; ++k) cost[k] = __popc(Lw[sidx] ^ S[16 + sidx - k]);
+            K = P1v - group_min2<LPP>(dp_step2<LPP>(dp, cost, K, maskUp, maskDn, negP1v, P2v));
+            // groups past the last image row recompute row H-1 and store the identical bytes (no predicate in the loop)
+            store_dp2(vchunk + sidx * D, dp);
+        };
+        if (x0 + U <= W) {  // full chunk (all but the one that holds the right image border): no per-pixel bound test
 #pragma unroll
-                for (int k = 0; k < 16; ++k) cost[k] = __popc(Lw[sidx] ^ S[16 + sidx - k]);
-                m = group_min<LPP>(dp_step<LPP>(dp, cost, m, lane, P1v, P2v));
-                if (valid) store_dp(vrow + (size_t)x * D, dp);
+            for (int t = 0; t < U; ++t) step(DX > 0 ? t : U - 1 - t);
+        } else {
+#pragma unroll
+            for (int t = 0; t < U; ++t) {
+                const int sidx = DX > 0 ? t : U - 1 - t;
+                if (x0 + sidx < W) step(sidx);  // warp-uniform: every group of the warp is at the same column
             }
         }
         if (DX > 0) {
@@ -276,17 +370,22 @@ __global__ void __launch_bounds__(128) aggregate_vertical_kernel(PathArgs a, int
     const uint32_t* clBase = a.cenL + (size_t)f * a.cenFrameStride + a.cenMargin + x0;
     const uint32_t* crBase = a.cenR + (size_t)f * a.cenFrameStride + a.cenMargin + x0 - 16 * lane - 16;
     uint8_t* vbase = volBase + (size_t)f * a.volFrameStride + (size_t)x0 * D + 16 * lane;
-    const uint32_t P1v = pack16(a.P1, a.P1), P2v = pack16(a.P2, a.P2);
+    const uint32_t maskUp = lane == 0 ? kSentinel2 : 0u, maskDn = lane == LPP - 1 ? kSentinel2 : 0u;
+    bool st[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) st[c] = valid && x0 + c < W;
 
     uint32_t dp[4][8];
-    uint32_t m[4];
+    uint32_t K[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        m[c] = 0;
+        K[c] = a.P1v;  // m = 0
 #pragma unroll
         for (int i = 0; i < 8; ++i) dp[c][i] = 0;
     }
-    for (int step = 0; step < H; ++step) {
+    uint8_t* vp = vbase + (dir > 0 ? (size_t)0 : (size_t)(H - 1) * W * D);  // row pointer, advanced by one image row per step
+    const ptrdiff_t vstep = dir > 0 ? (ptrdiff_t)W * D : -(ptrdiff_t)W * D;
+    for (int step = 0; step < H; ++step, vp += vstep) {
         const int y = dir > 0 ? step : H - 1 - step;
         const uint4 lw = __ldg(reinterpret_cast<const uint4*>(clBase + (size_t)y * a.cenStride));
         const uint32_t Lw[4] = {lw.x, lw.y, lw.z, lw.w};
@@ -310,8 +409,8 @@ __global__ void __launch_bounds__(128) aggregate_vertical_kernel(PathArgs a, int
             uint32_t cost[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) cost[k] = __popc(Lw[c] ^ S[16 + c - k]);
-            m[c] = group_min<LPP>(dp_step<LPP>(dp[c], cost, m[c], lane, P1v, P2v));
-            if (valid && x0 + c < W) store_dp(vbase + ((size_t)y * W + c) * D, dp[c]);
+            K[c] = a.P1v - group_min2<LPP>(dp_step2n<LPP>(dp[c], cost, K[c], maskUp, maskDn, a.negP1v, a.P2v));
+            if (st[c]) store_dp(vp + c * D, dp[c]);
         }
     }
 }
@@ -528,6 +627,9 @@ int launch_aggregate_range(cartb200_ctx* c, int n, int p0, int p1, cudaStream_t 
     a.P1 = c->cfg.p1;
     a.P2 = c->cfg.p2;
     a.dx = a.dy = 0;
+    a.P1v = (uint32_t)a.P1 * 0x10001u;
+    a.P2v = (uint32_t)a.P2 * 0x10001u;
+    a.negP1v = ((0x10000u - (uint32_t)a.P1) & 0xFFFFu) * 0x10001u;
     switch (c->D) {
         case 64: launch_paths_D<64>(c, a, n, p0, p1, s); break;
         case 128: launch_paths_D<128>(c, a, n, p0, p1, s); break;
