@@ -539,13 +539,13 @@ __device__ __forceinline__ void diagonal_body(const PathArgs& a, int dy, uint8_t
     const uint32_t* clF = a.cenL + (size_t)f * a.cenFrameStride + a.cenMargin;
     const uint32_t* crF = a.cenR + (size_t)f * a.cenFrameStride + a.cenMargin - 16 * lane - 16;
     uint8_t* vF = volBase + (size_t)f * a.volFrameStride + 16 * lane;
-    const uint32_t P1v = pack16(a.P1, a.P1), P2v = pack16(a.P2, a.P2);
+    const uint32_t maskUp = lane == 0 ? kSentinel2 : 0u, maskDn = lane == LPP - 1 ? kSentinel2 : 0u;
 
     uint32_t dp[4][8];
-    uint32_t m[4];
+    uint32_t K[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        m[c] = 0;
+        K[c] = a.P1v;  // m = 0
 #pragma unroll
         for (int i = 0; i < 8; ++i) dp[c][i] = 0;
     }
@@ -575,7 +575,7 @@ __device__ __forceinline__ void diagonal_body(const PathArgs& a, int dy, uint8_t
                 uint32_t cost[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) cost[k] = __popc((Lq[o + c] ^ Sq[o + 16 + c - k]) & mask);
-                m[c] = group_min<LPP>(dp_step<LPP>(dp[c], cost, m[c], lane, P1v, P2v));
+                K[c] = a.P1v - group_min2<LPP>(dp_step2n<LPP>(dp[c], cost, K[c], maskUp, maskDn, a.negP1v, a.P2v));
                 if (act) store_dp(vF + ((size_t)y * W + x) * D, dp[c]);
             }
         }
