@@ -121,18 +121,24 @@ class ClockSampler:
 
 
 def ncu_traffic_per_launch():
-    """dram__bytes_read + dram__bytes_write of one aggregation-path launch (64-frame batch) from the committed
-    `ncu --set full` summary (profiles/), or None."""
+    """dram__bytes_read + dram__bytes_write of one aggregation-path launch (64-frame batch, one direction) from the
+    committed `ncu --set full` summary (profiles/), or None.  The summaries also hold the fused two-direction launches
+    (twice the grid): only the single-direction launches of every kernel are averaged."""
     try:
         launches = []
-        for name in ("r01h_ncu_aggregate_horizontal_batch64.json", "r01b_ncu_sgm_batch64.json"):  # newest capture first
+        for name in ("r01m_ncu_aggregate_batch64.json", "r01h_ncu_aggregate_horizontal_batch64.json",
+                     "r01b_ncu_sgm_batch64.json"):  # newest capture first
             path = os.path.join(ROOT, "profiles", name)
             if os.path.exists(path):
-                launches = json.load(open(path))["launches"]
+                launches = [l for l in json.load(open(path))["launches"] if "aggregate_" in l["kernel"]]
                 break
+        grid = {}
+        for l in launches:
+            g = l.get("launch__grid_size []", 0)
+            grid[l["kernel"]] = min(grid.get(l["kernel"], g), g)
         tot = []
         for l in launches:
-            if "aggregate_" not in l["kernel"]:
+            if l.get("launch__grid_size []", 0) != grid[l["kernel"]]:
                 continue
             b = 0.0
             for k, v in l.items():
