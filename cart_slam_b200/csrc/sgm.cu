@@ -14,8 +14,6 @@
 #include <algorithm>
 #include <cstdlib>
 
-#define CARTB200_L2_PREFETCH 4       // horizontal kernel: chunks ahead
-#define CARTB200_L2_PREFETCH_ROWS 6  // vertical kernel: rows ahead
 #include "common.cuh"
 
 namespace cb {
@@ -103,6 +101,7 @@ struct PathArgs {
     int W, H, P1, P2;
     int dx, dy;
     uint32_t P1v, P2v, negP1v;  // (P1, P1), (P2, P2), (-P1, -P1) mod 2^16 as u16x2: read straight from the constant bank
+    int pfPixels, pfRows;       // L2 prefetch distances of the horizontal (pixels) and vertical (rows) kernels; 0 = off
 };
 
 __device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) { return hi * 65536u + lo; }
@@ -310,15 +309,14 @@ __device__ __forceinline__ void horizontal_body(const PathArgs& a, uint8_t* __re
             const int xn = DX > 0 ? x0 + U : x0 - U;
             load_words<U>(Ln, cl + xn);
             load_words<U>(Sn, cr + xn + (DX > 0 ? 16 : 0));
-#ifdef CARTB200_L2_PREFETCH
-            {  // and pull the chunk after next towards L2: the register prefetch alone leaves long-scoreboard stalls
-                const int xp = DX > 0 ? x0 + CARTB200_L2_PREFETCH * U : x0 - CARTB200_L2_PREFETCH * U;
+            if (a.pfPixels > 0) {  // and pull a chunk further ahead towards L2: the register prefetch alone leaves
+                                   // long-scoreboard stalls (15 % of the stall samples without it)
+                const int xp = DX > 0 ? x0 + a.pfPixels : x0 - a.pfPixels;
                 if (DX > 0 ? xp < W : xp >= 0) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(cl + xp));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(cr + xp + (DX > 0 ? 16 : 0)));
                 }
             }
-#endif
         } else {
             load_words<U>(Lw, cl + x0);
             load_words<U>(DX > 0 ? S + 16 : S, cr + x0 + (DX > 0 ? 16 : 0));
@@ -399,16 +397,14 @@ __global__ void __launch_bounds__(128) aggregate_vertical_kernel(PathArgs a, int
     const ptrdiff_t vstep = dir > 0 ? (ptrdiff_t)W * D : -(ptrdiff_t)W * D;
     for (int step = 0; step < H; ++step, vp += vstep) {
         const int y = dir > 0 ? step : H - 1 - step;
-#ifdef CARTB200_L2_PREFETCH_ROWS
-        {  // pull the census rows a few steps ahead towards L2 (the loads below are consumed immediately)
-            const int yp = dir > 0 ? y + CARTB200_L2_PREFETCH_ROWS : y - CARTB200_L2_PREFETCH_ROWS;
+        if (a.pfRows > 0) {  // pull the census rows a few steps ahead towards L2 (the loads below are consumed immediately)
+            const int yp = dir > 0 ? y + a.pfRows : y - a.pfRows;
             if (yp >= 0 && yp < H) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(clBase + (size_t)yp * a.cenStride));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(crBase + (size_t)yp * a.cenStride));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(crBase + (size_t)yp * a.cenStride + 19));
             }
         }
-#endif
         const uint4 lw = __ldg(reinterpret_cast<const uint4*>(clBase + (size_t)y * a.cenStride));
         const uint32_t Lw[4] = {lw.x, lw.y, lw.z, lw.w};
         // S[k] = shifted right census word (x0 - 16*lane - 16 + k), k = 0..19; cell (x0+c, j) uses S[16 + c - j]
@@ -652,6 +648,11 @@ int launch_aggregate_range(cartb200_ctx* c, int n, int p0, int p1, cudaStream_t 
     a.P1v = (uint32_t)a.P1 * 0x10001u;
     a.P2v = (uint32_t)a.P2 * 0x10001u;
     a.negP1v = ((0x10000u - (uint32_t)a.P1) & 0xFFFFu) * 0x10001u;
+    // CARTB200_PF_PIXELS / CARTB200_PF_ROWS (tuning aids): L2 prefetch distances, measured optimum as default
+    static const int pfPixels = getenv("CARTB200_PF_PIXELS") ? atoi(getenv("CARTB200_PF_PIXELS")) : 32;
+    static const int pfRows = getenv("CARTB200_PF_ROWS") ? atoi(getenv("CARTB200_PF_ROWS")) : 6;
+    a.pfPixels = pfPixels;
+    a.pfRows = pfRows;
     switch (c->D) {
         case 64: launch_paths_D<64>(c, a, n, p0, p1, s); break;
         case 128: launch_paths_D<128>(c, a, n, p0, p1, s); break;
