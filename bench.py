@@ -313,9 +313,13 @@ def main():
     import cart_slam_b200 as cb
 
     torch.cuda.set_device(local_rank)
+    # stdout carries the JSON line only: whatever libraries write to file descriptor 1 (NCCL prints its version banner
+    # there when NCCL_DEBUG >= VERSION; NCCL_DEBUG_FILE=/dev/stderr does not help when stderr cannot be re-opened)
+    # goes to stderr, and the JSON line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL's own log lines (its version banner at NCCL_DEBUG >= VERSION) go to stderr: stdout carries the JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hbm_peak, peak_src = load_peaks()
 
@@ -430,7 +434,8 @@ def main():
             "reference_gpu_kernels": ref_gpu,
             "library": cb.version(), "scratch_bytes": ctx.scratch_bytes(),
         }
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
