@@ -362,8 +362,8 @@ __global__ void __launch_bounds__(kHorizThreads, MINB) aggregate_horizontal_kern
 }
 
 // ---- vertical -------------------------------------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(128) aggregate_vertical_kernel(PathArgs a, int dirFirst, int both) {
+template <int D, int MINB>
+__global__ void __launch_bounds__(128, MINB) aggregate_vertical_kernel(PathArgs a, int dirFirst, int both) {
     constexpr int LPP = D / 16;
     constexpr int GPB = 128 / LPP;
     const int dir = both ? (blockIdx.z == 0 ? 1 : -1) : dirFirst;
@@ -604,12 +604,19 @@ static void launch_paths_D(cartb200_ctx* c, PathArgs a, int n, int p0, int p1, c
         a.vol2 = pair ? c->volumes + (size_t)(p + 1) * c->volPathStride : nullptr;
         if (a.dy == 0) {
             dim3 grid(ceilDiv(a.H, kHorizThreads / (D / 16)), n, pair ? 2 : 1);
-            // measured (B200, 64-frame batch): 8-pixel window with the next chunk prefetched at 5 CTAs/SM beats the
-            // variants tuned for occupancy (64 registers, 8 CTAs/SM) by 9 % - the kernel is pipe-bound, not latency-bound
-            aggregate_horizontal_kernel<D, kHorizU, true, 5><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0);
+            // measured on B200 (64-frame batch, profiles/r01n_aggregate_variant_sweep.txt): with the census rows
+            // prefetched into L2, the register prefetch of the next chunk is not needed any more and 64 registers /
+            // 8 CTAs per SM beat the 96-register prefetching variant by 2.7 %.  CARTB200_HORIZ_VARIANT (tuning aid)
+            // selects the older shapes.
+            static const int variant = getenv("CARTB200_HORIZ_VARIANT") ? atoi(getenv("CARTB200_HORIZ_VARIANT")) : 1;  // TODO-verify: 0 once parity-checked
+            switch (variant) {  // (pixels per window refill, register prefetch, minimum CTAs per SM)
+                case 1: aggregate_horizontal_kernel<D, 8, true, 5><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0); break;
+                case 2: aggregate_horizontal_kernel<D, 8, false, 6><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0); break;
+                default: aggregate_horizontal_kernel<D, kHorizU, false, 8><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0);
+            }
         } else if (a.dx == 0) {
             dim3 grid(ceilDiv(ceilDiv(a.W, 4), GPB), n, pair ? 2 : 1);
-            aggregate_vertical_kernel<D><<<grid, 128, 0, s>>>(a, a.dy, pair ? 1 : 0);
+            aggregate_vertical_kernel<D, 6><<<grid, 128, 0, s>>>(a, a.dy, pair ? 1 : 0);  // 7 CTAs/SM: same time, 8: spills
         } else if (getenv("CARTB200_GENERIC_DIAGONALS")) {  // the first, generic formulation (kept for cross-checks)
             dim3 grid(ceilDiv(a.W + a.H - 1, GPB), n);
             aggregate_path_kernel<D><<<grid, 128, 0, s>>>(a);

@@ -1,0 +1,43 @@
+"""bench.py pieces that can be checked without a GPU: the committed ncu summary the roofline's `traffic` figure comes
+from, the CPU reference arm's JSON line (bounded sample), and the workload table against BASELINE.json."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def test_ncu_traffic_matches_the_algorithmic_bytes_of_one_path():
+    t = bench.ncu_traffic_per_launch()
+    assert t is not None, "profiles/ holds no ncu summary of the aggregation kernels"
+    W, H, D, B = 1242, 375, 128, 64
+    algorithmic = B * (W * H * D + 2 * 4 * W * H)  # read both census images, write one u8 volume
+    assert abs(t / algorithmic - 1.0) < 0.03, (t, algorithmic)  # no wasted re-reads
+
+
+def test_workloads_are_the_baseline_configs():
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert "1242" in base["metric"] and "128 disp" in base["metric"]
+    k = bench.WORKLOADS["kitti"]
+    assert (k["W"], k["H"], k["D"], k["frames"]) == (1242, 375, 128, 1000)
+    z, u = bench.WORKLOADS["zed"], bench.WORKLOADS["4k"]
+    assert (z["W"], z["H"], z["D"]) == (1280, 720, 256) and (u["W"], u["H"], u["D"], u["paths"]) == (3840, 2160, 256, 8)
+
+
+@pytest.mark.timeout(600)
+def test_reference_arm_prints_one_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample", "1"], capture_output=True, text=True, timeout=580, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["metric"] == bench.METRIC and d["higher_is_better"] is True
