@@ -608,7 +608,7 @@ static void launch_paths_D(cartb200_ctx* c, PathArgs a, int n, int p0, int p1, c
             // prefetched into L2, the register prefetch of the next chunk is not needed any more and 64 registers /
             // 8 CTAs per SM beat the 96-register prefetching variant by 2.7 %.  CARTB200_HORIZ_VARIANT (tuning aid)
             // selects the older shapes.
-            static const int variant = getenv("CARTB200_HORIZ_VARIANT") ? atoi(getenv("CARTB200_HORIZ_VARIANT")) : 1;  // TODO-verify: 0 once parity-checked
+            static const int variant = getenv("CARTB200_HORIZ_VARIANT") ? atoi(getenv("CARTB200_HORIZ_VARIANT")) : 0;
             switch (variant) {  // (pixels per window refill, register prefetch, minimum CTAs per SM)
                 case 1: aggregate_horizontal_kernel<D, 8, true, 5><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0); break;
                 case 2: aggregate_horizontal_kernel<D, 8, false, 6><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0); break;
