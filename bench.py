@@ -126,7 +126,7 @@ def ncu_traffic_per_launch():
     (twice the grid): only the single-direction launches of every kernel are averaged."""
     try:
         launches = []
-        for name in ("r01m_ncu_aggregate_batch64.json", "r01h_ncu_aggregate_horizontal_batch64.json",
+        for name in ("r01o_ncu_aggregate_batch64.json", "r01m_ncu_aggregate_batch64.json", "r01h_ncu_aggregate_horizontal_batch64.json",
                      "r01b_ncu_sgm_batch64.json"):  # newest capture first
             path = os.path.join(ROOT, "profiles", name)
             if os.path.exists(path):
