@@ -12,7 +12,7 @@ OUT="$HERE/../_ref"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 [ -d "$R" ] || { echo "reference tree $R not present: keeping the prebuilt $OUT/libref.so"; exit 0; }
 mkdir -p "$OUT"
-if [ -f "$OUT/libref.so" ] && [ "$OUT/libref.so" -nt "$HERE/build_ref.sh" ] && [ "$OUT/libref.so" -nt "$HERE/shim.h" ] \
+if [ -f "$OUT/libref.so" ] && [ -f "$OUT/libref_host.so" ] && [ "$OUT/libref.so" -nt "$HERE/build_ref.sh" ] && [ "$OUT/libref.so" -nt "$HERE/shim.h" ] \
    && [ -z "$(find "$HERE" -name '*.inc' -newer "$OUT/libref.so")" ]; then exit 0; fi
 T=$(mktemp -d)
 trap 'rm -rf "$T"' EXIT
@@ -59,3 +59,10 @@ for n in derivative naive sp_planeseg interpolate contour planefit overlay overl
 done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/libref.so" "$T"/*.o -lcudart
 echo "built $OUT/libref.so"
+
+# The reference's HOST code for the plane parameters (persistence peak finder + histogram-peak provider), compiled
+# verbatim with g++ behind shim_host.h: runs on any CPU, pins the oracle's orc_find_peaks / orc_histogram_peak_update.
+{ echo "#include \"$HERE/shim_host.h\""; cut_ include/utils/peaks.hpp 8 22; echo; cut_ src/utils/peaks.cpp 3 73; echo;
+  echo "namespace cart {"; cut_ src/modules/planeseg/planeseg.cu 404 458; echo "}"; cat "$HERE/harness_host.inc"; } > "$T/host_params.cpp"
+${CXX:-g++} -O2 -std=c++17 -fPIC -w -shared -o "$OUT/libref_host.so" "$T/host_params.cpp"
+echo "built $OUT/libref_host.so"
