@@ -13,7 +13,8 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 [ -d "$R" ] || { echo "reference tree $R not present: keeping the prebuilt $OUT/libref.so"; exit 0; }
 mkdir -p "$OUT"
 if [ -f "$OUT/libref.so" ] && [ -f "$OUT/libref_host.so" ] && [ "$OUT/libref.so" -nt "$HERE/build_ref.sh" ] && [ "$OUT/libref.so" -nt "$HERE/shim.h" ] \
-   && [ -z "$(find "$HERE" -name '*.inc' -newer "$OUT/libref.so")" ]; then exit 0; fi
+   && [ "$OUT/libref_host.so" -nt "$HERE/build_ref.sh" ] && [ "$OUT/libref_host.so" -nt "$HERE/shim_host.h" ] \
+   && [ -z "$(find "$HERE" -name '*.inc' -newer "$OUT/libref.so")" ] && [ -z "$(find "$HERE" -name '*.inc' -newer "$OUT/libref_host.so")" ]; then exit 0; fi
 T=$(mktemp -d)
 trap 'rm -rf "$T"' EXIT
 cut_() { sed -n "$2,$3p" "$R/$1"; }
@@ -64,5 +65,9 @@ echo "built $OUT/libref.so"
 # verbatim with g++ behind shim_host.h: runs on any CPU, pins the oracle's orc_find_peaks / orc_histogram_peak_update.
 { echo "#include \"$HERE/shim_host.h\""; cut_ include/utils/peaks.hpp 8 22; echo; cut_ src/utils/peaks.cpp 3 73; echo;
   echo "namespace cart {"; cut_ src/modules/planeseg/planeseg.cu 404 458; echo "}"; cat "$HERE/harness_host.inc"; } > "$T/host_params.cpp"
-${CXX:-g++} -O2 -std=c++17 -fPIC -w -shared -o "$OUT/libref_host.so" "$T/host_params.cpp"
+# ... and its KITTI calibration line parser (src/sources/kitti.cpp:11-12 camera ids, :18-85 addLeadingZeros,
+# KITTICameraCalibration, readLine) for the on-disk source of the host layer
+{ echo "#include <cstdint>"; echo "#include <string>"; echo "#include <algorithm>"; cut_ src/sources/kitti.cpp 11 12; cut_ src/sources/kitti.cpp 18 85;
+  cat "$HERE/harness_kitti.inc"; } > "$T/host_kitti.cpp"
+${CXX:-g++} -O2 -std=c++17 -fPIC -w -shared -o "$OUT/libref_host.so" "$T/host_params.cpp" "$T/host_kitti.cpp"
 echo "built $OUT/libref_host.so"

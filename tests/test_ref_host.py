@@ -75,3 +75,45 @@ def test_histogram_peak_update_matches_the_reference(ref):
             assert list(p) == list(cb.histogram_peak_update(h, start)[1]), "product (plane_params.cpp) differs from the reference"
             changed += list(p) != start
     assert changed > 20  # the update path, not only the early returns, is exercised
+
+
+def test_kitti_calibration_matches_the_reference_parser(ref, tmp_path):
+    """The host layer's KITTIDataSource (calib.txt -> Q) against the reference's own readLine (kitti.cpp:32-85) on several
+    calibration files: the KITTI odometry layout, other numbers / exponents, reordered lines, junk lines."""
+    cv2 = pytest.importorskip("cv2")
+    from cart_slam_b200 import host
+
+    rng = np.random.default_rng(5)
+
+    def calib_text(k):
+        rows = {}
+        for cam in range(4):
+            fx = 700 + 30 * k + rng.random()
+            cx, cy = 600 + rng.random() * 10, 180 + rng.random() * 10
+            tx = 0.0 if cam == 0 else float(rng.normal(0, 200))
+            v = [fx, 0, cx, tx, 0, fx, cy, rng.normal(), 0, 0, 1, rng.normal() * 1e-3]
+            fmt = "%.12e" if k % 2 == 0 else "%.6f"
+            rows[cam] = f"P{cam}: " + " ".join(fmt % x for x in v)
+        order = [0, 1, 2, 3] if k < 3 else [3, 1, 2, 0]
+        lines = [rows[c] for c in order] + ["Tr: " + " ".join("%.6e" % x for x in rng.normal(size=12))]
+        if k == 4:
+            lines = ["# comment without separator", "Q9 1 2 3"] + lines
+        return "\n".join(lines) + "\n"
+
+    f = ref.ref_kitti_q
+    f.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_void_p]
+    for k in range(6):
+        text = calib_text(k)
+        d = tmp_path / f"c{k}" / "sequences" / "00"
+        (d / "image_2").mkdir(parents=True)
+        (d / "image_3").mkdir()
+        (d / "calib.txt").write_text(text)
+        cv2.imwrite(str(d / "image_2" / "000000.png"), np.zeros((12, 16, 3), np.uint8))
+        cv2.imwrite(str(d / "image_3" / "000000.png"), np.zeros((12, 16, 3), np.uint8))
+        W, H, Q = host.open_source({"type": "kitti", "path": str(tmp_path / f"c{k}"), "sequence": 0})
+        q = np.zeros(16, np.float32)
+        assert f(text.encode(), 1.0, 1.0, q.ctypes.data_as(C.c_void_p)) == 0
+        assert (W, H) == (16, 12)
+        assert np.array_equal(np.asarray(Q, np.float32).reshape(16), q), k
+    # a file without the right camera line
+    assert f(b"P2: 1 0 1 1 0 1 1 0 0 0 1 0\n", 1.0, 1.0, np.zeros(16, np.float32).ctypes.data_as(C.c_void_p)) == -1
