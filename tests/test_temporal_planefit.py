@@ -274,3 +274,37 @@ def test_gpu_overlays_bit_exact(inp):
         seed = np.full(bgr.shape, 77, np.uint8)
         got = ctx.overlay_superpixel_boundaries(dev(bgr), dev(labels), out=dev(seed)).cpu().numpy()
         assert np.array_equal(got, po.overlay_boundaries(bgr, labels, out=seed))
+
+
+# ---- randomised properties of the oracle's temporal vote (hypothesis) -------------------------------------------
+def test_temporal_vote_properties_randomised():
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=40, deadline=None)
+    @hyp.given(st.integers(0, 2 ** 31 - 1), st.integers(1, 4), st.integers(3, 24), st.integers(3, 24))
+    def prop(seed, count, H, W):
+        rng = np.random.default_rng(seed)
+        d = rng.integers(-6, 36, (H, W)).astype(np.int16)
+        d[rng.random((H, W)) < 0.2] = -32768
+        pp = [rng.integers(0, 3, (H, W)).astype(np.uint8) for _ in range(count)]
+        pf = [rng.integers(-32768, 32768, (H, W, 2)).astype(np.int16) if rng.random() < 0.3 else
+              rng.integers(-96, 97, (H, W, 2)).astype(np.int16) for _ in range(count)]
+        unsm, sm = po.classify_temporal(d, 1, 30, -3, 1, pp, pf)
+        assert np.array_equal(sm, np_temporal(unsm, pp, pf, 0))          # independent restatement, any flow
+        assert sm.max() <= 2
+        # a pixel can only be UNKNOWN after the naive vote if neither H nor V received a vote
+        assert ((sm == 2) <= (unsm == 2)).all()
+        # zero flow and a history equal to the current classes changes nothing for decided pixels
+        zero = [np.zeros((H, W, 2), np.int16)] * count
+        _, same = po.classify_temporal(d, 1, 30, -3, 1, [unsm] * count, zero)
+        assert np.array_equal(same[unsm != 2], unsm[unsm != 2])
+        # superpixel weighting: one label for the whole image -> the image-wide majority of the voted planes
+        d2 = np.stack([d, d], axis=2)
+        lab = np.zeros((H, W), np.uint16)
+        _, planes = po.sp_planeseg_temporal(d2, lab, 1, 1, 30, -3, 1, pp, pf)
+        voted = np_temporal(unsm, pp, pf, 1)
+        assert np.array_equal(planes, np_sp_assign(lab, voted, 1))
+        assert len(np.unique(planes)) == 1
+
+    prop()
