@@ -14,7 +14,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libcartb200.so")
+_LIB_PATH = os.environ.get("CARTB200_LIB") or os.path.join(_HERE, "libcartb200.so")  # CARTB200_LIB: experiments with another build
 
 OK, E_ARG, E_SHAPE, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 DISPARITY_INVALID = -32768
