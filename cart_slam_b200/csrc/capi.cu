@@ -199,6 +199,12 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
         return fail(CARTB200_E_CUDA);
     }
     cudaGetDevice(&dev);
+    c->device = dev;
+    if (sgm_set_kernel_attributes() != cudaSuccess || post_set_kernel_attributes() != cudaSuccess ||
+        sp_set_kernel_attributes() != cudaSuccess) {
+        c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(cudaGetLastError());
+        return fail(CARTB200_E_CUDA);
+    }
     c->W = cfg->width;
     c->H = cfg->height;
     c->D = cfg->num_disparities;

@@ -70,6 +70,7 @@ struct cartb200_ctx {
     long long launches = 0;
     size_t scratchBytes = 0;
     int W = 0, H = 0, D = 0, B = 0, P = 0;
+    int device = 0;  // the CUDA device the context was created on; every entry point checks it is current
     // SGM scratch
     uint8_t* grayL = nullptr;   // [B][H][grayPitch]
     uint8_t* grayR = nullptr;
@@ -148,5 +149,9 @@ int launch_overlay_planes(cartb200_ctx* c, Img<const uint8_t> bgr, Img<const uin
 int launch_overlay_boundaries(cartb200_ctx* c, Img<const uint8_t> bgr, Img<const uint16_t> labels, Img<uint8_t> out, cudaStream_t s);
 int launch_depth(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<float> xyz, const float* q16Host, cudaStream_t s);
 int launch_border_map(cartb200_ctx* c, Img<const uint16_t> labels, Img<uint8_t> border, cudaStream_t s);
+// per-device kernel attributes (dynamic shared memory limits), applied by cartb200_create on the context's device
+cudaError_t sgm_set_kernel_attributes();
+cudaError_t post_set_kernel_attributes();
+cudaError_t sp_set_kernel_attributes();
 void build_sp_tile_tables(int W, int H, std::vector<int>& tileMap, std::vector<uint32_t>& tab);
 }  // namespace cb

@@ -71,6 +71,10 @@ __global__ void __launch_bounds__(256) interpolate_kernel(ImgBatch<const int16_t
     }
 }
 
+cudaError_t post_set_kernel_attributes() {  // per device, from cartb200_create
+    return cudaFuncSetAttribute(interpolate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 int launch_interpolate_from(cartb200_ctx* c, int n, ImgBatch<const int16_t> src, ImgBatch<int16_t> dst, int radius,
                             int iterations, int minD, int maxD, cudaStream_t s) {
     const int pad = radius - 1, S = 64 + 2 * pad;
@@ -78,11 +82,6 @@ int launch_interpolate_from(cartb200_ctx* c, int n, ImgBatch<const int16_t> src,
     if (smem > 200 * 1024) {
         c->err = "interpolate: smoothing radius too large for shared memory";
         return CARTB200_E_UNSUPPORTED;
-    }
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(interpolate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr = true;
     }
     dim3 grid(ceilDiv(c->W, 64), ceilDiv(c->H, 64), n);
     interpolate_kernel<<<grid, 256, smem, s>>>(src, dst, c->W, c->H, radius, iterations, minD, maxD);

@@ -863,6 +863,22 @@ __global__ void __launch_bounds__(128, 5) wta_walk_kernel(WtaArgs a) {
     }
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set from cartb200_create for the context's device
+template <int D>
+static cudaError_t wta_attributes_D() {
+    cudaError_t e = cudaFuncSetAttribute(wta_walk_kernel<D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kWtaDepth * 4 * 128 * sizeof(uint4)));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(wta_walk_kernel<D, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kWtaDepth * 8 * 128 * sizeof(uint4)));
+}
+cudaError_t sgm_set_kernel_attributes() {
+    cudaError_t e;
+    if ((e = wta_attributes_D<64>()) != cudaSuccess) return e;
+    if ((e = wta_attributes_D<128>()) != cudaSuccess) return e;
+    return wta_attributes_D<256>();
+}
+
 template <int D>
 static int launch_wta_D(cartb200_ctx* c, WtaArgs& a, int n, cudaStream_t s) {
     constexpr int GPB = 128 / (D / 16);
@@ -877,23 +893,11 @@ static int launch_wta_D(cartb200_ctx* c, WtaArgs& a, int n, cudaStream_t s) {
     a.nItems = (int)(rows * a.nSeg);
     CB_CHECK_CUDA(c, cudaMemsetAsync(c->wtaR, 0xFF, (size_t)n * c->H * c->rkPitch * sizeof(uint32_t), s));
     dim3 grid(ceilDiv(a.nItems, GPB));
-    if (c->P == 4) {
-        static bool attr4 = false;
-        if (!attr4) {
-            cudaFuncSetAttribute(wta_walk_kernel<D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kWtaDepth * 4 * 128 * sizeof(uint4)));
-            attr4 = true;
-        }
+    // (the dynamic shared memory limit of these kernels is raised per device in sgm_set_kernel_attributes)
+    if (c->P == 4)
         wta_walk_kernel<D, 4><<<grid, 128, kWtaDepth * 4 * 128 * sizeof(uint4), s>>>(a);
-    } else {
-        static bool attr = false;
-        if (!attr) {
-            cudaFuncSetAttribute(wta_walk_kernel<D, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kWtaDepth * 8 * 128 * sizeof(uint4)));
-            attr = true;
-        }
+    else
         wta_walk_kernel<D, 8><<<grid, 128, kWtaDepth * 8 * 128 * sizeof(uint4), s>>>(a);
-    }
     CB_LAUNCH_CHECK(c);
     return CARTB200_OK;
 }
