@@ -264,9 +264,9 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
             return fail(CARTB200_E_UNSUPPORTED);
         }
         c->spLabelPitch = alignUp(W * 2, 128);
-        if ((rc = devAlloc(c, &c->spLabels, B * H * c->spLabelPitch))) return fail(rc);
+        if ((rc = devAlloc(c, &c->spLabels, B * 2 * H * c->spLabelPitch))) return fail(rc);  // two planes per slot
         if ((rc = devAlloc(c, &c->spYcc, B * H * W * 4))) return fail(rc);
-        if ((rc = devAlloc(c, &c->spStats, B * (size_t)(c->maxLabels + 1) * 24 * sizeof(double)))) return fail(rc);
+        if ((rc = devAlloc(c, &c->spStats, B * (size_t)(c->maxLabels + 1) * 40 * sizeof(double)))) return fail(rc);
         if ((rc = devAlloc(c, &c->spNew, B * H * W * sizeof(uint16_t)))) return fail(rc);
         if ((rc = devAlloc(c, &c->spList, B * H * W * sizeof(uint32_t)))) return fail(rc);
         if ((rc = devAlloc(c, &c->spCount, B * sizeof(int)))) return fail(rc);
@@ -695,7 +695,7 @@ int cartb200_superpixels_set_labels(cartb200_ctx* c, int slot, const uint16_t* l
         if (c) c->err = "superpixels_set_labels: bad arguments";
         return CARTB200_E_ARG;
     }
-    CB_CHECK_CUDA(c, cudaMemcpy2DAsync((char*)c->spLabels + (size_t)slot * c->spLabelPitch * c->H, c->spLabelPitch, labels,
+    CB_CHECK_CUDA(c, cudaMemcpy2DAsync((char*)c->spLabels + (size_t)slot * 2 * c->spLabelPitch * c->H, c->spLabelPitch, labels,
                                        lp, (size_t)c->W * 2, c->H, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return CARTB200_OK;
 }

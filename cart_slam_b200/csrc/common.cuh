@@ -93,10 +93,10 @@ struct cartb200_ctx {
     uint32_t* votes = nullptr;     // [B][maxLabels][4]
     // superpixels
     int maxLabels = 0, spBlocksPerRow = 0;
-    uint16_t* spLabels = nullptr;  // [B][H][spLabelPitch/2] persistent
+    uint16_t* spLabels = nullptr;  // [B][2][H][spLabelPitch/2] persistent labels in plane 0, plane 1 = ping-pong partner
     size_t spLabelPitch = 0;
     uint8_t* spYcc = nullptr;  // [B][H][W][4] Y,Cr,Cb,border-flag scratch
-    double* spStats = nullptr;     // [B][maxLabels][kStatDoubles]
+    double* spStats = nullptr;     // [B]{[labels][16] records, [labels][8] stored costs, [labels][16] deltas}
     uint16_t* spNew = nullptr;     // [B][H*W] decided label per list entry
     uint32_t* spList = nullptr;    // [B][H*W] listed border pixels (x | y << 16)
     int* spCount = nullptr;        // [B] move-list lengths
