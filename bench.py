@@ -254,10 +254,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="frames per batched launch (SGM stages); superpixel slots = sequence chunks")
     ap.add_argument("--pipeline", type=int, default=None, help="1 = superpixel pipeline (headline), 0 = naive")
     ap.add_argument("--cpu-sample", type=int, default=6)
-    ap.add_argument("--sp-exact", type=int, default=1,
-                    help="1 (default): superpixel label costs in the reference's operation order - labels bit-identical to the "
-                         "oracle over whole chains; 0: cost differences (relaxation 1.65x faster, >= 99.9 %% per-frame label "
-                         "agreement - the tolerance the metric allows)")
+    ap.add_argument("--sp-exact", type=int, default=1, help="accepted for old command lines; ignored (the approximate mode is gone)")
     args = ap.parse_args()
     global W, H, D, METRIC
     wl = WORKLOADS[args.workload]
@@ -279,8 +276,7 @@ def main():
                        if args.pipeline == 1 else "naive planeseg (kitti-naive-segmentation.json), ")
                     + ("histogram_peak provider" if provider == 1 else "static ranges h [1,30) v [-3,1)"),
         "frames_per_gpu": args.frames, "batch": args.batch, "pipeline": "superpixel" if args.pipeline == 1 else "naive",
-        "superpixel_costs": ("exact: reference operation order, labels bit-identical to the oracle" if args.sp_exact else
-                             "fast: cost differences, >= 99.9 % per-frame label agreement") if args.pipeline == 1 else None,
+        "superpixel_costs": "exact: reference operation order, labels bit-identical to the oracle" if args.pipeline == 1 else None,
         "l2": "inputs and intermediates per step (>= 2.8 GB images, 3.8 GB cost volumes per batch) exceed the 126 MB L2",
     }
 
@@ -333,7 +329,7 @@ def main():
     torch.cuda.synchronize()
 
     cfg = cb.Config(W, H, max_batch=args.batch, num_disparities=D, min_disparity=MIN_DISP, paths=n_paths, smoothing_radius=2,
-                    smoothing_iterations=1, enable_superpixels=args.pipeline == 1, sp_block_size=sp_block, sp_exact=bool(args.sp_exact))
+                    smoothing_iterations=1, enable_superpixels=args.pipeline == 1, sp_block_size=sp_block)
     ctx = cb.Context(cfg)
     opts = cb.SequenceOptions(pipeline=args.pipeline, provider=provider, static_params=(1, 30, -3, 1), sp_initial_iterations=24,
                               sp_iterations=8, sp_reset_iterations=64)

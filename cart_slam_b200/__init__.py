@@ -157,7 +157,7 @@ class Config:
     sp_progressive_compactness_cost: float = 0.0
     sp_image_weight: float = 1.5
     sp_disparity_weight: float = 1.0
-    sp_exact: bool = True  # label costs in the reference's operation order: labels bit-identical to the oracle; False = faster cost differences
+    sp_exact: bool = True  # kept for ABI compatibility, ignored: label costs are always in the reference's operation order
 
     def to_c(self) -> _CConfig:
         c = _CConfig()

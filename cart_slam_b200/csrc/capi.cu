@@ -267,9 +267,6 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
         if ((rc = devAlloc(c, &c->spLabels, B * 2 * H * c->spLabelPitch))) return fail(rc);  // two planes per slot
         if ((rc = devAlloc(c, &c->spYcc, B * H * W * 4))) return fail(rc);
         if ((rc = devAlloc(c, &c->spStats, B * (size_t)(c->maxLabels + 1) * 40 * sizeof(double)))) return fail(rc);
-        if ((rc = devAlloc(c, &c->spNew, B * H * W * sizeof(uint16_t)))) return fail(rc);
-        if ((rc = devAlloc(c, &c->spList, B * H * W * sizeof(uint32_t)))) return fail(rc);
-        if ((rc = devAlloc(c, &c->spCount, B * sizeof(int)))) return fail(rc);
         if ((rc = devAlloc(c, &c->votes, B * (size_t)c->maxLabels * 4 * sizeof(uint32_t)))) return fail(rc);
         {
             std::vector<int> tileMap;
@@ -309,9 +306,6 @@ void cartb200_destroy(cartb200_ctx* c) {
     cudaFree(c->spLabels);
     cudaFree(c->spYcc);
     cudaFree(c->spStats);
-    cudaFree(c->spNew);
-    cudaFree(c->spList);
-    cudaFree(c->spCount);
     cudaFree(c->spTileMap);
     cudaFree(c->spTileTab);
     if (c->seq) {

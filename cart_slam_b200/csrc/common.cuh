@@ -97,9 +97,6 @@ struct cartb200_ctx {
     size_t spLabelPitch = 0;
     uint8_t* spYcc = nullptr;  // [B][H][W][4] Y,Cr,Cb,border-flag scratch
     double* spStats = nullptr;     // [B]{[labels][16] records, [labels][8] stored costs, [labels][16] deltas}
-    uint16_t* spNew = nullptr;     // [B][H*W] decided label per list entry
-    uint32_t* spList = nullptr;    // [B][H*W] listed border pixels (x | y << 16)
-    int* spCount = nullptr;        // [B] move-list lengths
     int* spTileMap = nullptr;      // [tilesY][tilesX] index into spTileTab, -1 = interior tile
     uint32_t* spTileTab = nullptr; // [edge tiles][66*66] source pixel (y << 16 | x) of the reference's label tile
     // sequence runner scratch (lazy)

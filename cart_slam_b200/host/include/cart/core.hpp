@@ -95,6 +95,7 @@ class ThreadPool {
     ~ThreadPool();
     void post(std::function<void()> fn);
     void join();  // waits until the queue is drained and all workers are idle
+    static bool onWorkerThread();  // true on a thread owned by (any) ThreadPool
 
    private:
     void work();
@@ -219,8 +220,17 @@ class SystemModule {
 class SyncWrapperSystemModule : public SystemModule {
    public:
     explicit SyncWrapperSystemModule(const std::string& name) : SystemModule(name) {}
-    std::future<system_data_t> run(System& system, SystemRunData& data) override;  // posts runInternal to the pool
+    std::future<system_data_t> run(System& system, SystemRunData& data) override;  // runInternal on a pool thread
     virtual system_data_t runInternal(System& system, SystemRunData& data) = 0;
+
+   private:
+    // Runs enter runInternal in run-id order.  The reference serialises the stateful modules with a mutex only, so with
+    // several frames in flight their warm-started state (superpixel labels, running histograms) depends on thread
+    // timing; here the order is fixed, which makes the module layer reproduce the sequence runner for any worker count.
+    system_data_t runOrdered(System& system, SystemRunData& data);
+    std::mutex orderMutex;
+    std::condition_variable orderCv;
+    uint32_t lastRun = 0;  // id of the last run that went through this module
 };
 
 // ---- system ----------------------------------------------------------------------------------------
@@ -269,6 +279,7 @@ class System : public DataContainer {
     void verifyDependencies();
     void waitForDependencies(const std::vector<module_dependency_t>& deps, std::shared_ptr<SystemRunData> data);
     bool verifiedDependencies = false;
+    std::vector<std::shared_ptr<SystemModule>> runOrder;  // modules in dependency order (same-run dependencies first)
     const size_t runRetention, concurrentRunLimit;
     ThreadPool threadPool;
     uint32_t runId = 0;

@@ -1,6 +1,7 @@
 // C entry point of the module layer, used by the tests (ctypes) and by integrators who want the whole
 // reference-shaped pipeline behind one call: builds a System from a JSON module list (the reference's
 // config/modules/*.json schema), feeds it `n` frames from host memory in id order, returns the planes.
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <exception>
@@ -54,7 +55,11 @@ int cartb200_host_run_config_ex(const char* modules_json, int skip_out_of_scope,
             std::memcpy(in.Q, q16, sizeof(in.Q));
             source->setCameraIntrinsics(in);
         }
-        auto system = std::make_shared<System>(source);
+        // CARTB200_HOST_WORKERS (testing aid): size of the System's thread pool (default CARTSLAM_WORKER_THREADS)
+        size_t workers = CARTSLAM_WORKER_THREADS;
+        if (const char* w = std::getenv("CARTB200_HOST_WORKERS"))
+            if (std::atoi(w) > 0) workers = (size_t)std::atoi(w);
+        auto system = std::make_shared<System>(source, workers);
         config::applyModuleConfigText(modules_json, system, skip_out_of_scope != 0);
         const size_t px = (size_t)width * height;
         std::deque<std::pair<uint32_t, std::future<void>>> inflight;
@@ -121,7 +126,11 @@ int cartb200_host_run_source(const char* source_json, const char* modules_json, 
         if (height) *height = size.height;
         if (q16_out) std::memcpy(q16_out, source->getCameraIntrinsics().Q, 16 * sizeof(float));
         if (!modules_json) return 0;
-        auto system = std::make_shared<System>(source);
+        // CARTB200_HOST_WORKERS (testing aid): size of the System's thread pool (default CARTSLAM_WORKER_THREADS)
+        size_t workers = CARTSLAM_WORKER_THREADS;
+        if (const char* w = std::getenv("CARTB200_HOST_WORKERS"))
+            if (std::atoi(w) > 0) workers = (size_t)std::atoi(w);
+        auto system = std::make_shared<System>(source, workers);
         config::applyModuleConfigText(modules_json, system, skip_out_of_scope != 0);
         const size_t px = (size_t)size.width * size.height;
         int done = 0;

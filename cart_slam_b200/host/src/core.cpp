@@ -82,7 +82,13 @@ void ThreadPool::post(std::function<void()> fn) {
     cv.notify_one();
 }
 
+namespace {
+thread_local bool tlsPoolWorker = false;
+}
+bool ThreadPool::onWorkerThread() { return tlsPoolWorker; }
+
 void ThreadPool::work() {
+    tlsPoolWorker = true;
     for (;;) {
         std::function<void()> fn;
         {
@@ -171,10 +177,37 @@ std::shared_ptr<DataElement> MemoryDataSource::getNextInternal(void* stream) {
 }
 
 // ---- modules ---------------------------------------------------------------------------------------
+// The reference posts runInternal to the pool and chains non-blocking continuations (module.cpp:7-19).  Here the caller
+// of run() inside System::run already owns a pool worker and blocks on the future, so a second post would need a second
+// worker for the same module: with few workers every one of them would be such a waiter and nothing could run.  On a
+// pool thread the work is therefore done inline and a ready future is returned; other callers get the posted task.
+system_data_t SyncWrapperSystemModule::runOrdered(System& system, SystemRunData& data) {
+    {
+        std::unique_lock<std::mutex> lock(orderMutex);
+        // ids below the expected one (a second System, a restarted source) are let through unordered
+        orderCv.wait(lock, [&] { return data.id <= lastRun + 1; });
+    }
+    struct Advance {
+        SyncWrapperSystemModule* m;
+        uint32_t id;
+        ~Advance() {
+            {
+                std::lock_guard<std::mutex> lock(m->orderMutex);
+                if (id > m->lastRun) m->lastRun = id;
+            }
+            m->orderCv.notify_all();
+        }
+    } advance{this, data.id};  // also on an exception: later runs must not wait for a failed one
+    return runInternal(system, data);
+}
+
 std::future<system_data_t> SyncWrapperSystemModule::run(System& system, SystemRunData& data) {
-    auto task = std::make_shared<std::packaged_task<system_data_t()>>([this, &system, &data] { return runInternal(system, data); });
+    auto task = std::make_shared<std::packaged_task<system_data_t()>>([this, &system, &data] { return runOrdered(system, data); });
     auto future = task->get_future();
-    system.getThreadPool().post([task] { (*task)(); });
+    if (ThreadPool::onWorkerThread())
+        (*task)();
+    else
+        system.getThreadPool().post([task] { (*task)(); });
     return future;
 }
 
@@ -202,6 +235,32 @@ void System::verifyDependencies() {
             if (dataProvidedBy.find(dep.name) == dataProvidedBy.end())
                 throw std::invalid_argument("Module " + module->name + " requires data " + dep.name +
                                             " which is not provided by any module");
+    // Post order = dependency order over the same-run dependencies (stable: configuration order among independent
+    // modules).  The pool is FIFO and a task only ever waits for tasks posted before it (same run: earlier in this
+    // order; earlier runs: posted earlier), so the oldest unfinished task is never blocked - no deadlock for any
+    // worker count >= 1, which the reference gets from its non-blocking future continuations (cartslam.cpp:255-302).
+    runOrder.clear();
+    std::vector<bool> placed(modules.size(), false);
+    for (size_t done = 0; done < modules.size();) {
+        bool progress = false;
+        for (size_t i = 0; i < modules.size(); ++i) {
+            if (placed[i]) continue;
+            bool ready = true;
+            for (const auto& dep : modules[i]->getRequiredData()) {
+                if (dep.runOffset != 0) continue;
+                auto provider = dataProvidedBy[dep.name];
+                if (provider == modules[i]) continue;
+                for (size_t j = 0; j < modules.size(); ++j)
+                    if (modules[j] == provider && !placed[j]) ready = false;
+            }
+            if (!ready) continue;
+            placed[i] = true;
+            runOrder.push_back(modules[i]);
+            ++done;
+            progress = true;
+        }
+        if (!progress) throw std::invalid_argument("The modules' same-run dependencies form a cycle");
+    }
     verifiedDependencies = true;
 }
 
@@ -259,7 +318,7 @@ std::future<void> System::run() {
     auto pending = std::make_shared<Pending>();
     pending->left = modules.size();
     auto future = pending->done.get_future();
-    for (auto module : modules) {
+    for (auto module : runOrder) {
         // one task per module and frame: wait for its inputs, run it, publish its outputs (cartslam.cpp:255-302)
         threadPool.post([this, module, runData, pending] {
             try {

@@ -61,12 +61,10 @@ typedef struct cartb200_config {
     int sp_block_size; /* 12 */
     double sp_direct_clique_cost, sp_diagonal_clique_cost;
     double sp_compactness_weight, sp_progressive_compactness_cost, sp_image_weight, sp_disparity_weight;
-    /* 1 (default): the label costs are evaluated in the reference's operation order (gaussian.cu:30-43,
-     *    compactness.cu:28-35, contourrelaxation.cu:102-144) with a fully specified logarithm: the labels are
-     *    bit-identical to the scalar oracle, also over arbitrarily long warm-started chains;
-     * 0: cost DIFFERENCES with one logarithm per label (relaxation 1.65x faster; labels agree with the oracle to
-     *    >= 99.9 % per frame from identical input labels, but the last bits of the costs differ, so two chains drift
-     *    apart over many frames - as two runs of the reference itself do). */
+    /* Kept for ABI compatibility, ignored.  The label costs are always evaluated in the reference's operation order
+     * (gaussian.cu:30-43, compactness.cu:28-35, contourrelaxation.cu:102-144) with a fully specified logarithm: the
+     * labels are bit-identical to the scalar oracle, also over arbitrarily long warm-started chains.  (A faster
+     * approximate mode existed while the exact evaluation was slower than it; it is gone.) */
     int sp_exact;
 } cartb200_config;
 

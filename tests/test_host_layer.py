@@ -86,10 +86,15 @@ def test_naive_json_pipeline_matches_sequence_runner(sequential):
 
 
 @pytest.mark.gpu
-def test_superpixel_json_pipeline_matches_sequence_runner():
+@pytest.mark.parametrize("workers,sequential", [(None, True), (1, False), (2, False), (3, True)])
+def test_superpixel_json_pipeline_matches_sequence_runner(workers, sequential, monkeypatch):
+    """Also the scheduler's liveness: the shipped module order is not a dependency order (superpixels first), and with
+    1-3 pool workers and up to 12 frames in flight every worker used to end up waiting for a module that could not start."""
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
+    if workers:
+        monkeypatch.setenv("CARTB200_HOST_WORKERS", str(workers))
     W, H, D, n = 160, 64, 64, 19
     L, R, _ = _frames(W, H, D, n, tint=True)
     # kitti-planeseg.json shape (module order as shipped: superpixels first, dependencies resolve the order)
@@ -103,7 +108,7 @@ def test_superpixel_json_pipeline_matches_sequence_runner():
          "update_interval": 5, "reset_interval": 2, "use_temporal_smoothing": True},
         {"type": "bev_planeseg_visualization"},
     ]
-    out = host.run_config(modules, L, R, skip_out_of_scope=True, want_labels=True, want_disparity=True)
+    out = host.run_config(modules, L, R, skip_out_of_scope=True, sequential=sequential, want_labels=True, want_disparity=True)
     cfg = cb.Config(W, H, max_batch=3, num_disparities=D, smoothing_radius=2, smoothing_iterations=1, sp_block_size=8)
     opts = cb.SequenceOptions(pipeline=1, provider=1, update_interval=5, reset_interval=2, sp_initial_iterations=6,
                               sp_iterations=3, sp_reset_iterations=8)

@@ -36,7 +36,7 @@ def main():
     ap.add_argument("--disp", type=int, default=128)
     ap.add_argument("--block", type=int, default=12)
     ap.add_argument("--tag", default="")
-    ap.add_argument("--sp-exact", action="store_true", help="superpixel costs in the reference's operation order")
+    ap.add_argument("--sp-exact", action="store_true", help="accepted for old command lines; ignored (always exact)")
     ap.add_argument("--once", action="store_true", help="run every stage exactly once (for ncu captures)")
     args = ap.parse_args()
     if args.once:
@@ -52,7 +52,7 @@ def main():
     L = torch.from_numpy(np.stack([f[0] for f in fr])).cuda()
     R = torch.from_numpy(np.stack([f[1] for f in fr])).cuda()
     cfg = cb.Config(W, H, max_batch=B, num_disparities=D, paths=args.paths, smoothing_radius=2, smoothing_iterations=1,
-                    sp_block_size=args.block, sp_exact=args.sp_exact)
+                    sp_block_size=args.block)
     res = {}
     with cb.Context(cfg) as ctx:
         res["gray_census"] = timeit(lambda: ctx.sgm_gray_census(L, R))
