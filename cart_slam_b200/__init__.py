@@ -106,6 +106,11 @@ def _load():
     lib.cartb200_region_inliers.argtypes = [vp, vp, sz, vp, sz, i, vp, i, C.c_double, vp, vp]
     lib.cartb200_run_sequence_host.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp, vp]
     lib.cartb200_run_sequence_device.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp, vp, vp]
+    lib.cartb200_run_sequence_phase1_device.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp, vp, vp]
+    lib.cartb200_run_sequence_phase2_device.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp]
+    lib.cartb200_sequence_parameters.argtypes = [C.POINTER(_CSeqOpts), i, vp, vp]
+    lib.cartb200_run_sequence_phase1_host.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp, vp]
+    lib.cartb200_run_sequence_phase2_host.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp]
     lib.cartb200_debug_ref_tile_i32.restype = C.c_int32
     lib.cartb200_debug_ref_tile_i32.argtypes = [vp] + [i] * 11 + [C.c_long, C.c_int32, i, i]
     lib.cartb200_debug_median9.restype = C.c_uint32
@@ -122,8 +127,23 @@ EXPORTED_SYMBOLS = [
     "cartb200_derivative", "cartb200_depth", "cartb200_naive_derivative", "cartb200_classify", "cartb200_superpixels_reset",
     "cartb200_superpixels_relax", "cartb200_superpixels_set_labels", "cartb200_superpixels_border_map",
     "cartb200_sp_planeseg", "cartb200_histogram_peak_update", "cartb200_default_sequence_opts",
-    "cartb200_run_sequence_host", "cartb200_run_sequence_device", "cartb200_debug_ref_tile_i32",
+    "cartb200_run_sequence_host", "cartb200_run_sequence_device", "cartb200_run_sequence_phase1_device",
+    "cartb200_run_sequence_phase2_device", "cartb200_run_sequence_phase1_host", "cartb200_run_sequence_phase2_host",
+    "cartb200_sequence_parameters", "cartb200_debug_ref_tile_i32",
 ]
+
+
+def sequence_parameters(opts: "SequenceOptions", hist: np.ndarray) -> np.ndarray:
+    """The reference's parameter bookkeeping over a whole sequence (CPU, no GPU needed): hist = [n, 256] int32 per-frame
+    histograms in id order starting at opts.start_id; returns [n, 4] int32 {hStart, hEnd, vStart, vEnd} per frame."""
+    hist = np.ascontiguousarray(hist, dtype=np.int32)
+    assert hist.ndim == 2 and hist.shape[1] == 256
+    out = np.zeros((hist.shape[0], 4), np.int32)
+    o = opts.to_c()
+    rc = _lib.cartb200_sequence_parameters(C.byref(o), hist.shape[0], hist.ctypes.data, out.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"cartb200_sequence_parameters: bad arguments ({rc})")
+    return out
 
 
 def version() -> str:
@@ -541,6 +561,57 @@ class Context:
         self._check(_lib.cartb200_run_sequence_host(self._h, C.byref(o), n, ptr(left), ptr(right), ptr(planes_out),
                                                     ptr(disparity_out) if disparity_out is not None else None))
         return (planes_out, disparity_out) if want_disparity else planes_out
+
+    @staticmethod
+    def _hptr(a):
+        if isinstance(a, np.ndarray):
+            assert a.flags.c_contiguous
+            return a.ctypes.data
+        return a.data_ptr()
+
+    def run_sequence_phase1_host(self, opts: SequenceOptions, left, right) -> np.ndarray:
+        """Phase 1 with HOST image buffers (numpy or pinned CPU tensors); returns the histograms [n, 256]."""
+        n = left.shape[0]
+        assert tuple(left.shape) == (n, self.H, self.W, 3) and tuple(right.shape) == tuple(left.shape)
+        hist = np.zeros((n, 256), np.int32)
+        o = opts.to_c()
+        self._check(_lib.cartb200_run_sequence_phase1_host(self._h, C.byref(o), n, self._hptr(left), self._hptr(right),
+                                                           hist.ctypes.data, None))
+        return hist
+
+    def run_sequence_phase2_host(self, opts: SequenceOptions, params: np.ndarray, planes_out=None):
+        """Phase 2 with a HOST plane buffer."""
+        params = np.ascontiguousarray(params, dtype=np.int32)
+        n = params.shape[0]
+        if planes_out is None:
+            planes_out = np.empty((n, self.H, self.W), np.uint8)
+        o = opts.to_c()
+        self._check(_lib.cartb200_run_sequence_phase2_host(self._h, C.byref(o), n, params.ctypes.data, self._hptr(planes_out)))
+        return planes_out
+
+    def run_sequence_phase1(self, opts: SequenceOptions, left, right) -> np.ndarray:
+        """Phase 1 of the sharded runner on device buffers; returns the per-frame histograms [n, 256] int32 (host)."""
+        torch = self.torch
+        n, lp, pitch, fs = self._img(left, torch.uint8, 3)
+        _, rp, _, _ = self._img(right, torch.uint8, 3)
+        assert pitch == self.W * 3 and fs == self.W * self.H * 3, "device sequence buffers must be tightly packed"
+        hist = np.zeros((n, 256), np.int32)
+        o = opts.to_c()
+        self._check(_lib.cartb200_run_sequence_phase1_device(self._h, C.byref(o), n, lp, rp, hist.ctypes.data, None, self._stream()))
+        return hist
+
+    def run_sequence_phase2(self, opts: SequenceOptions, params: np.ndarray, planes_out=None, device=None):
+        """Phase 2: params = [n, 4] int32 (host) for the frames of the preceding phase 1; returns device planes."""
+        torch = self.torch
+        params = np.ascontiguousarray(params, dtype=np.int32)
+        n = params.shape[0]
+        assert params.shape == (n, 4)
+        if planes_out is None:
+            planes_out = torch.empty((n, self.H, self.W), dtype=torch.uint8, device=device or "cuda")
+        o = opts.to_c()
+        self._check(_lib.cartb200_run_sequence_phase2_device(self._h, C.byref(o), n, params.ctypes.data, planes_out.data_ptr(),
+                                                             self._stream()))
+        return planes_out
 
     def run_sequence_device(self, opts: SequenceOptions, left, right, want_disparity=False, planes_out=None):
         torch = self.torch

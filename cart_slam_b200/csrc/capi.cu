@@ -21,6 +21,7 @@ namespace {
 
 struct SeqScratch {
     int nFrames = 0, pipeline = -1;
+    int phase1Frames = 0, phase1Pipeline = -1;  // what a completed phase 1 left in deriv / labels
     uint8_t* inL = nullptr;     // staged inputs (host variant) [n][H][W*3]
     uint8_t* inR = nullptr;
     int16_t* disp = nullptr;    // [B] or [n] frames, tight pitch
@@ -771,9 +772,16 @@ void spUpdate(HistState& st, const cartb200_sequence_opts& o, int id, const int3
     std::memcpy(outParams, st.params + 2, 4 * sizeof(int32_t));
 }
 
+// phase 0: the whole pipeline.  phase 1: everything up to the per-frame histograms (copied to histOut, HOST, n x 256, the
+// channel the pipeline's parameter provider consumes), derivative / label images stay in the context.  phase 2: plane
+// parameters given per frame (paramsIn, HOST, n x 4) -> vote / classify on what phase 1 left behind.  Two phases are
+// what lets one sequence be sharded over several GPUs with the histogram_peak provider: the
+// running histogram crosses the shard boundaries, the per-frame histograms do not.
 int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const uint8_t* inL, const uint8_t* inR,
-                bool inputsOnHost, uint8_t* planesOut, int16_t* dispOut, bool outputsOnHost, cudaStream_t userStream) {
-    if (!c || !o || n < 1 || !inL || !inR || !planesOut) {
+                bool inputsOnHost, uint8_t* planesOut, int16_t* dispOut, bool outputsOnHost, cudaStream_t userStream,
+                int phase = 0, int32_t* histOut = nullptr, const int32_t* paramsIn = nullptr) {
+    if (!c || !o || n < 1 || (phase != 2 && (!inL || !inR)) || (phase != 1 && !planesOut) || (phase == 1 && !histOut) ||
+        (phase == 2 && !paramsIn)) {
         if (c) c->err = "run_sequence: bad arguments";
         return CARTB200_E_ARG;
     }
@@ -802,6 +810,11 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
     const size_t bgrFrame = W * H * 3, pxFrame = W * H;
     int rc;
     cudaStream_t s = userStream;
+    if (phase == 2 && (q->phase1Frames != n || q->phase1Pipeline != o->pipeline)) {
+        c->err = "run_sequence phase 2: no matching phase 1 (same context, pipeline and frame count) precedes it";
+        return CARTB200_E_ARG;
+    }
+    if (phase != 2) q->phase1Frames = 0;
     if (!q->copyStream) {
         CB_CHECK_CUDA(c, cudaStreamCreateWithFlags(&q->copyStream, cudaStreamNonBlocking));
         for (auto& e : q->evIn) CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -823,7 +836,7 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
     }
     // superpixel pipeline: derivative and label images are kept per frame (the relaxation stream lags behind the
     // SGM stream, and the histogram-peak provider needs them again in the second phase)
-    const size_t nStore = sp ? (size_t)n : B;
+    const size_t nStore = (sp || phase != 0) ? (size_t)n : B;
     if ((rc = ensureCap(c, &q->disp, &q->dispCap, pxFrame * 2 * (dispOut ? (size_t)n : B)))) return rc;
     if ((rc = ensureCap(c, &q->deriv, &q->derivCap, pxFrame * (sp ? 4 : 2) * nStore))) return rc;
     if (sp && (rc = ensureCap(c, &q->labels, &q->labelsCap, pxFrame * 2 * nStore))) return rc;
@@ -833,6 +846,8 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
     if (q->nFrames < n) {
         cudaFreeHost(q->histHost);
         cudaFreeHost(q->paramsHost);
+        q->histHost = q->paramsHost = nullptr;  // a failed allocation below must not leave stale pointers behind
+        q->nFrames = 0;
         const size_t cap = std::max<size_t>((size_t)n, B);
         CB_CHECK_CUDA(c, cudaMallocHost((void**)&q->histHost, cap * 512 * sizeof(int32_t)));
         CB_CHECK_CUDA(c, cudaMallocHost((void**)&q->paramsHost, cap * 4 * sizeof(int32_t)));
@@ -864,38 +879,52 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
             CB_CHECK_CUDA(c, cudaEventRecord(q->evIn[(b0 / B) & 1], q->copyStream));
             return CARTB200_OK;
         };
-        if ((rc = upload(0))) return rc;
+        if (phase != 2 && (rc = upload(0))) return rc;
         for (int b0 = 0; b0 < n; b0 += (int)B) {
             const int nb = std::min<int>((int)B, n - b0);
-            if (inputsOnHost) CB_CHECK_CUDA(c, cudaStreamWaitEvent(s, q->evIn[(b0 / B) & 1], 0));
-            if ((rc = upload(b0 + (int)B))) return rc;
             int16_t* dB = dispOut ? dispDev + pxFrame * b0 : dispDev;
-            if ((rc = cartb200_disparity(c, nb, devL + bgrFrame * b0, devR + bgrFrame * b0, W * 3, bgrFrame, dB, W * 2,
-                                         pxFrame * 2, s)))
-                return rc;
-            if ((rc = launch_naive_derivative(c, nb, ImgBatch<const int16_t>{dB, W * 2, pxFrame * 2},
-                                              ImgBatch<int16_t>{q->deriv, W * 2, pxFrame * 2}, q->hist + 256 * (size_t)b0, s)))
-                return rc;
-            int32_t* ph = q->paramsHost + 4 * (size_t)b0;
-            if (peak) {
-                CB_CHECK_CUDA(c, cudaMemcpyAsync(q->histHost + 256 * (size_t)b0, q->hist + 256 * (size_t)b0,
-                                                 (size_t)nb * 256 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-                CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
-                for (int i = 0; i < nb; ++i)
-                    naiveUpdate(hs, *o, o->start_id + b0 + i, q->histHost + 256 * (size_t)(b0 + i), ph + 4 * i);
-            } else {
-                for (int i = 0; i < nb; ++i) std::memcpy(ph + 4 * i, hs.params + 2, 4 * sizeof(int32_t));
-            }
-            if ((rc = uploadParams(c, nb, ph, s))) return rc;
-            if ((rc = launch_classify(c, nb, ImgBatch<const int16_t>{q->deriv, W * 2, pxFrame * 2}, 1, 0, c->paramsDev,
-                                      ImgBatch<uint8_t>{planesDev + pxFrame * b0, W, pxFrame}, s)))
-                return rc;
-            if (outputsOnHost) {
-                CB_CHECK_CUDA(c, cudaMemcpyAsync(planesOut + pxFrame * b0, planesDev + pxFrame * b0, pxFrame * nb,
-                                                 cudaMemcpyDeviceToHost, s));
-                if (dispOut)
+            // derivative images: one batch (whole pipeline) or all frames (phase 1 keeps them for phase 2)
+            int16_t* vB = phase == 0 ? q->deriv : q->deriv + pxFrame * b0;
+            if (phase != 2) {
+                if (inputsOnHost) CB_CHECK_CUDA(c, cudaStreamWaitEvent(s, q->evIn[(b0 / B) & 1], 0));
+                if ((rc = upload(b0 + (int)B))) return rc;
+                if ((rc = cartb200_disparity(c, nb, devL + bgrFrame * b0, devR + bgrFrame * b0, W * 3, bgrFrame, dB, W * 2,
+                                             pxFrame * 2, s)))
+                    return rc;
+                if ((rc = launch_naive_derivative(c, nb, ImgBatch<const int16_t>{dB, W * 2, pxFrame * 2},
+                                                  ImgBatch<int16_t>{vB, W * 2, pxFrame * 2}, q->hist + 256 * (size_t)b0, s)))
+                    return rc;
+                if (outputsOnHost && dispOut)
                     CB_CHECK_CUDA(c, cudaMemcpyAsync(dispOut + pxFrame * b0, dB, pxFrame * 2 * nb, cudaMemcpyDeviceToHost, s));
             }
+            if (phase == 1) continue;
+            const int32_t* ph = paramsIn ? paramsIn + 4 * (size_t)b0 : q->paramsHost + 4 * (size_t)b0;
+            if (phase == 0) {
+                int32_t* pw = q->paramsHost + 4 * (size_t)b0;
+                if (peak) {
+                    CB_CHECK_CUDA(c, cudaMemcpyAsync(q->histHost + 256 * (size_t)b0, q->hist + 256 * (size_t)b0,
+                                                     (size_t)nb * 256 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+                    CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
+                    for (int i = 0; i < nb; ++i)
+                        naiveUpdate(hs, *o, o->start_id + b0 + i, q->histHost + 256 * (size_t)(b0 + i), pw + 4 * i);
+                } else {
+                    for (int i = 0; i < nb; ++i) std::memcpy(pw + 4 * i, hs.params + 2, 4 * sizeof(int32_t));
+                }
+            }
+            if ((rc = uploadParams(c, nb, ph, s))) return rc;
+            if ((rc = launch_classify(c, nb, ImgBatch<const int16_t>{vB, W * 2, pxFrame * 2}, 1, 0, c->paramsDev,
+                                      ImgBatch<uint8_t>{planesDev + pxFrame * b0, W, pxFrame}, s)))
+                return rc;
+            if (outputsOnHost)
+                CB_CHECK_CUDA(c, cudaMemcpyAsync(planesOut + pxFrame * b0, planesDev + pxFrame * b0, pxFrame * nb,
+                                                 cudaMemcpyDeviceToHost, s));
+        }
+        if (phase == 1) {
+            CB_CHECK_CUDA(c, cudaMemcpyAsync(histOut, q->hist, (size_t)n * 256 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
+            q->phase1Frames = n;
+            q->phase1Pipeline = 0;
+            return CARTB200_OK;
         }
         if (outputsOnHost || inputsOnHost) CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
         return CARTB200_OK;
@@ -906,7 +935,38 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
     const int firstId = o->start_id, lastId = o->start_id + n - 1;
     const int k0 = firstId / R, k1 = lastId / R;  // chunk range
     const int nChunks = k1 - k0 + 1;
-    if (!peak) {  // static ranges are the same for every frame: upload them once
+    // vote + assign for all frames from the derivative / label images kept per frame, `params` = HOST n x 4
+    bool planesCopied = false;
+    auto votePhase = [&](const int32_t* params) -> int {
+        for (int b0 = 0, bi = 0; b0 < n; b0 += (int)B, ++bi) {
+            const int nb = std::min<int>((int)B, n - b0);
+            if ((rc = uploadParams(c, nb, params + 4 * (size_t)b0, s))) return rc;
+            if ((rc = launch_sp_planeseg(c, nb, ImgBatch<const int16_t>{q->deriv + pxFrame * 2 * b0, W * 4, pxFrame * 4},
+                                         ImgBatch<const uint16_t>{q->labels + pxFrame * b0, W * 2, pxFrame * 2}, c->maxLabels,
+                                         c->paramsDev, ImgBatch<uint8_t>{q->unsm, W, pxFrame},
+                                         ImgBatch<uint8_t>{planesDev + pxFrame * b0, W, pxFrame}, s)))
+                return rc;
+            if (outputsOnHost) {  // download this batch while the next one is voted
+                CB_CHECK_CUDA(c, cudaEventRecord(q->evIn[bi & 1], s));
+                CB_CHECK_CUDA(c, cudaStreamWaitEvent(q->copyStream, q->evIn[bi & 1], 0));
+                CB_CHECK_CUDA(c, cudaMemcpyAsync(planesOut + pxFrame * b0, planesDev + pxFrame * b0, pxFrame * nb,
+                                                 cudaMemcpyDeviceToHost, q->copyStream));
+            }
+        }
+        if (outputsOnHost) {
+            CB_CHECK_CUDA(c, cudaEventRecord(q->evStart, q->copyStream));
+            CB_CHECK_CUDA(c, cudaStreamWaitEvent(s, q->evStart, 0));
+            planesCopied = true;
+        }
+        return CARTB200_OK;
+    };
+    if (phase == 2) {
+        if ((rc = votePhase(paramsIn))) return rc;
+        if (outputsOnHost) CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
+        return CARTB200_OK;
+    }
+    const bool deferVote = peak || phase == 1;  // parameters are only known once every frame's histogram is
+    if (!deferVote) {  // static ranges are the same for every frame: upload them once
         for (size_t j = 0; j < B; ++j) std::memcpy(q->paramsHost + 4 * j, hs.params + 2, 4 * sizeof(int32_t));
         if ((rc = uploadParams(c, (int)B, q->paramsHost, s))) return rc;
     }
@@ -1034,7 +1094,7 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
                 if ((rc = launch_sp_relax(c, nb, slots, its, sl, sv, true, so, spS))) return rc;
             }
         }
-        if (!peak) {
+        if (!deferVote) {
             // static ranges: vote + assign right away (the same ranges for every frame of the batch)
             const ImgBatch<const int16_t> vBc{vB.data, vB.pitch, vB.frameStride, vB.inner, vB.outerStride};
             const ImgBatch<const uint16_t> lBc{lB.data, lB.pitch, lB.frameStride, lB.inner, lB.outerStride};
@@ -1043,39 +1103,31 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
                 return rc;
         }
     }
-    if (peak) CB_CHECK_CUDA(c, cudaMemcpyAsync(q->histHost, q->hist, histRows * 512 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (deferVote) CB_CHECK_CUDA(c, cudaMemcpyAsync(q->histHost, q->hist, histRows * 512 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CB_CHECK_CUDA(c, cudaEventRecord(q->evSpDone, spS));
     CB_CHECK_CUDA(c, cudaStreamWaitEvent(s, q->evSpDone, 0));
-    bool planesCopied = false;
-    if (peak) {
+    if (deferVote) {
         // second phase: parameters in id order, then vote + assign for every frame
         CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
         std::vector<int32_t> hv(256);
         for (int i = 0; i < n; ++i) {
             const int32_t* h = q->histHost + 512 * histPos[(size_t)i];
             for (int b = 0; b < 256; ++b) hv[b] = h[2 * b];  // channel 0 = vertical (sp_planeseg.cu:358-359)
-            spUpdate(hs, *o, firstId + i, hv.data(), q->paramsHost + 4 * (size_t)i);
+            if (phase == 1)
+                std::memcpy(histOut + 256 * (size_t)i, hv.data(), 256 * sizeof(int32_t));
+            else
+                spUpdate(hs, *o, firstId + i, hv.data(), q->paramsHost + 4 * (size_t)i);
         }
-        for (int b0 = 0, bi = 0; b0 < n; b0 += (int)B, ++bi) {
-            const int nb = std::min<int>((int)B, n - b0);
-            if ((rc = uploadParams(c, nb, q->paramsHost + 4 * (size_t)b0, s))) return rc;
-            if ((rc = launch_sp_planeseg(c, nb, ImgBatch<const int16_t>{q->deriv + pxFrame * 2 * b0, W * 4, pxFrame * 4},
-                                         ImgBatch<const uint16_t>{q->labels + pxFrame * b0, W * 2, pxFrame * 2}, c->maxLabels,
-                                         c->paramsDev, ImgBatch<uint8_t>{q->unsm, W, pxFrame},
-                                         ImgBatch<uint8_t>{planesDev + pxFrame * b0, W, pxFrame}, s)))
-                return rc;
-            if (outputsOnHost) {  // download this batch while the next one is voted
-                CB_CHECK_CUDA(c, cudaEventRecord(q->evIn[bi & 1], s));
-                CB_CHECK_CUDA(c, cudaStreamWaitEvent(q->copyStream, q->evIn[bi & 1], 0));
-                CB_CHECK_CUDA(c, cudaMemcpyAsync(planesOut + pxFrame * b0, planesDev + pxFrame * b0, pxFrame * nb,
-                                                 cudaMemcpyDeviceToHost, q->copyStream));
+        if (phase == 1) {
+            if (outputsOnHost && dispOut) {
+                CB_CHECK_CUDA(c, cudaMemcpyAsync(dispOut, dispDev, pxFrame * 2 * n, cudaMemcpyDeviceToHost, s));
+                CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
             }
+            q->phase1Frames = n;
+            q->phase1Pipeline = 1;
+            return CARTB200_OK;
         }
-        if (outputsOnHost) {
-            CB_CHECK_CUDA(c, cudaEventRecord(q->evStart, q->copyStream));
-            CB_CHECK_CUDA(c, cudaStreamWaitEvent(s, q->evStart, 0));
-            planesCopied = true;
-        }
+        if ((rc = votePhase(q->paramsHost))) return rc;
     }
     if (outputsOnHost) {
         if (!planesCopied) CB_CHECK_CUDA(c, cudaMemcpyAsync(planesOut, planesDev, pxFrame * n, cudaMemcpyDeviceToHost, s));
@@ -1097,6 +1149,46 @@ int cartb200_run_sequence_host(cartb200_ctx* c, const cartb200_sequence_opts* o,
 int cartb200_run_sequence_device(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const uint8_t* l,
                                  const uint8_t* r, uint8_t* planes, int16_t* disp, void* stream) {
     return runSequence(c, o, n, l, r, false, planes, disp, false, (cudaStream_t)stream);
+}
+
+int cartb200_run_sequence_phase1_device(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const uint8_t* l,
+                                        const uint8_t* r, int32_t* hist_host, int16_t* disp, void* stream) {
+    return runSequence(c, o, n, l, r, false, nullptr, disp, false, (cudaStream_t)stream, 1, hist_host, nullptr);
+}
+
+int cartb200_run_sequence_phase2_device(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const int32_t* params_host,
+                                        uint8_t* planes, void* stream) {
+    return runSequence(c, o, n, nullptr, nullptr, false, planes, nullptr, false, (cudaStream_t)stream, 2, nullptr, params_host);
+}
+
+int cartb200_run_sequence_phase1_host(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const uint8_t* l,
+                                      const uint8_t* r, int32_t* hist_host, int16_t* disp) {
+    return runSequence(c, o, n, l, r, true, nullptr, disp, true, nullptr, 1, hist_host, nullptr);
+}
+
+int cartb200_run_sequence_phase2_host(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const int32_t* params_host,
+                                      uint8_t* planes) {
+    return runSequence(c, o, n, nullptr, nullptr, false, planes, nullptr, true, nullptr, 2, nullptr, params_host);
+}
+
+int cartb200_sequence_parameters(const cartb200_sequence_opts* o, int n, const int32_t* hist, int32_t* params) {
+    if (!o || n < 0 || (n > 0 && (!hist || !params)) || (o->pipeline != 0 && o->pipeline != 1) || o->update_interval < 1 ||
+        o->reset_interval < 1)
+        return CARTB200_E_ARG;
+    HistState hs;
+    if (o->provider != 1) {
+        hs.params[2] = o->static_params[0];
+        hs.params[3] = o->static_params[1];
+        hs.params[4] = o->static_params[2];
+        hs.params[5] = o->static_params[3];
+    }
+    for (int i = 0; i < n; ++i) {
+        if (o->pipeline == 0)
+            naiveUpdate(hs, *o, o->start_id + i, hist + 256 * (size_t)i, params + 4 * (size_t)i);
+        else
+            spUpdate(hs, *o, o->start_id + i, hist + 256 * (size_t)i, params + 4 * (size_t)i);
+    }
+    return CARTB200_OK;
 }
 
 }  // extern "C"

@@ -274,6 +274,36 @@ int cartb200_run_sequence_device(cartb200_ctx* ctx, const cartb200_sequence_opts
                                  const uint8_t* left_bgr_dev, const uint8_t* right_bgr_dev, uint8_t* planes_dev,
                                  int16_t* disparity_dev, void* stream);
 
+/* ---- one sequence sharded over several GPUs (BASELINE.json configs[4]) ------------------
+ * The superpixel chain is cut at every reset frame, so a shard that starts at id 1 or at a multiple of
+ * sp_reset_iterations (opts->start_id) reproduces the unsharded labels.  The plane parameters of the histogram_peak
+ * providers, however, come from a RUNNING histogram over all earlier frames (planeseg.cu:379-403,
+ * sp_planeseg.cu:352-388), which crosses shard boundaries.  The two-pass scheme:
+ *   phase 1 (per shard)    everything up to the per-frame histograms; hist_host = n x 256 int32 (HOST; naive pipeline:
+ *                          the frame's derivative histogram, superpixel pipeline: its vertical channel).  Derivative and
+ *                          label images of the n frames stay inside the context.
+ *   exchange               the ranks all-gather their histograms (a few hundred KB) - the only data-path collective
+ *                          besides the final result gather;
+ *   cartb200_sequence_parameters (CPU, any rank)   the reference's bookkeeping over the WHOLE sequence in id order:
+ *                          hist = n_total x 256, opts->start_id = id of the first row; params = n_total x 4
+ *                          {hStart, hEnd, vStart, vEnd} per frame (static provider: the static ranges);
+ *   phase 2 (per shard)    params_host = the shard's n x 4 slice -> classify / vote + assign -> planes_dev n x H x W.
+ * phase 2 must follow a phase 1 of the same context, pipeline and n.  Running phase 1, cartb200_sequence_parameters and
+ * phase 2 on one whole sequence equals cartb200_run_sequence_device bit for bit. */
+int cartb200_run_sequence_phase1_device(cartb200_ctx* ctx, const cartb200_sequence_opts* opts, int n_frames,
+                                        const uint8_t* left_bgr_dev, const uint8_t* right_bgr_dev, int32_t* hist_host,
+                                        int16_t* disparity_dev, void* stream);
+int cartb200_run_sequence_phase2_device(cartb200_ctx* ctx, const cartb200_sequence_opts* opts, int n_frames,
+                                        const int32_t* params_host, uint8_t* planes_dev, void* stream);
+/* the same two phases with HOST image / plane buffers (uploads and downloads overlapped with compute inside the calls) */
+int cartb200_run_sequence_phase1_host(cartb200_ctx* ctx, const cartb200_sequence_opts* opts, int n_frames,
+                                      const uint8_t* left_bgr_host, const uint8_t* right_bgr_host, int32_t* hist_host,
+                                      int16_t* disparity_host);
+int cartb200_run_sequence_phase2_host(cartb200_ctx* ctx, const cartb200_sequence_opts* opts, int n_frames,
+                                      const int32_t* params_host, uint8_t* planes_host);
+int cartb200_sequence_parameters(const cartb200_sequence_opts* opts, int n_frames, const int32_t* hist_host,
+                                 int32_t* params_host);
+
 /* CPU evaluation of the closed-form reference-tile mapping used by the kernels (no GPU needed); lets the
  * CPU test-suite check it against the oracle's literal copyToShared simulation.  Returns the value the
  * reference's shared tile holds at local (lx, ly) of block (bx, by) for an int32 image. */
