@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """bench.py - stereo frames/s (1242x375, 128 disparities) through disparity -> planeseg on B200.
 
-A "step" is one pass of the hot path over one KITTI-shaped synthetic stereo sequence (BASELINE.json
-configs[1]: 1000 frames, full disparity + superpixels + planeseg on one B200).  With N GPUs every rank
-processes its own sequence (frames shard naturally; the only collective is the final result gather),
-so scaling is "weak".
+A "step" is one pass of the hot path over one KITTI-shaped synthetic stereo sequence.
+  N = 1: BASELINE.json configs[1] - 1000 frames, full disparity + superpixels + planeseg on one B200.
+  N > 1: BASELINE.json configs[4] - ONE 10,000-frame sequence sharded over the ranks at superpixel reset frames
+         (cart_slam_b200.parallel.plan_shards).  The histogram_peak parameters come from a running histogram that
+         crosses the shard boundaries, hence the two-pass scheme of SURVEY.md section 8(e): phase 1 per shard ->
+         all-gather of the per-frame histograms (256 int32 per frame) -> the reference's parameter schedule on the CPU
+         -> phase 2 per shard -> gather of the plane labels to rank 0.  The result equals the unsharded run bit for bit
+         (tests/test_sharded_sequence.py).  Total work is fixed: "strong" scaling; the gather is timed separately.
 
   value  : frames/s with the sequence already resident in HBM (cartb200_run_sequence_device)
   e2e    : frames/s through the C ABI call that takes HOST buffers (cartb200_run_sequence_host):
            pinned host -> device copies of both images and the device -> host copy of the plane labels
            are inside the timed region
-  roofline    : the path-aggregation kernel (dominant), algorithmic bytes / CUDA-event time vs measured HBM peak
+  roofline    : the path-aggregation kernels (the largest HBM-bound group of the step; the metric's "% HBM peak"),
+                algorithmic bytes / CUDA-event time vs measured HBM peak
   cpu_baseline: OpenCV CPU StereoSGBM (MODE_HH4, all host threads) + the scalar oracle for the planeseg
                 half, on a bounded sample of the same frames
 
@@ -70,7 +75,9 @@ def make_frames(n_frames: int, sequence_id: int):
     for i in range(n_frames):
         L[i], R[i], _ = seq.frame(i + 1)
     try:
-        np.savez(cache, L=L, R=R)
+        tmp = cache + f".{os.getpid()}.tmp.npz"
+        np.savez(tmp, L=L, R=R)
+        os.replace(tmp, cache)  # several ranks may generate the same sequence at once
     except Exception:
         pass
     return L, R
@@ -120,18 +127,30 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _sha16(path):
+    import hashlib
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()[:16]
+
+
 def ncu_traffic_per_launch():
-    """dram__bytes_read + dram__bytes_write of one aggregation-path launch (64-frame batch, one direction) from the
-    committed `ncu --set full` summary (profiles/), or None.  The summaries also hold the fused two-direction launches
-    (twice the grid): only the single-direction launches of every kernel are averaged."""
+    """dram__bytes_read + dram__bytes_write of one aggregation-path launch (64-frame batch, one direction) from the newest
+    committed `ncu --set full` summary under profiles/ - DRAM counters cannot be read inside an unprofiled run.  A summary
+    carries the hash of the kernel source it was captured from ("source_sha16" of csrc/sgm.cu); when the source has
+    changed since, the number is stale and None is reported with the reason.  Returns (bytes or None, note)."""
     try:
-        launches = []
-        for name in ("r01o_ncu_aggregate_batch64.json", "r01m_ncu_aggregate_batch64.json", "r01h_ncu_aggregate_horizontal_batch64.json",
-                     "r01b_ncu_sgm_batch64.json"):  # newest capture first
-            path = os.path.join(ROOT, "profiles", name)
-            if os.path.exists(path):
-                launches = [l for l in json.load(open(path))["launches"] if "aggregate_" in l["kernel"]]
-                break
+        import glob
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_aggregate_batch64.json")), reverse=True)
+        if not cands:
+            return None, "no ncu summary of the aggregation kernels under profiles/"
+        doc = json.load(open(cands[0]))
+        name = os.path.basename(cands[0])
+        sha = doc.get("source_sha16")
+        cur = _sha16(os.path.join(ROOT, "cart_slam_b200", "csrc", "sgm.cu"))
+        if sha is None:
+            return None, f"{name} carries no source hash: cannot tell whether it matches the kernels that ran"
+        if sha != cur:
+            return None, f"{name} was captured from another revision of csrc/sgm.cu ({sha} != {cur}): stale, not reported"
+        launches = [l for l in doc["launches"] if "aggregate_" in l["kernel"]]
         grid = {}
         for l in launches:
             g = l.get("launch__grid_size []", 0)
@@ -146,9 +165,9 @@ def ncu_traffic_per_launch():
                     unit = k[k.index("[") + 1:k.index("]")]
                     b += v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
             tot.append(b)
-        return sum(tot) / len(tot) if tot else None
-    except Exception:
-        return None
+        return (sum(tot) / len(tot) if tot else None), f"{name} (ncu --set full, same source revision)"
+    except Exception as e:
+        return None, f"unreadable ncu summary: {e}"
 
 
 def reference_gpu_kernels():
@@ -251,6 +270,9 @@ def main():
     ap.add_argument("--impl", default="cartb200", choices=["cartb200", "reference"])
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=None, help="frames per sequence (BASELINE.json configs[1]: 1000)")
+    ap.add_argument("--total-frames", type=int, default=10000,
+                    help="N > 1: length of the ONE sequence sharded over the ranks (BASELINE.json configs[4]: 10000); frame id i "
+                         "shows distinct frame (i - 1) mod --frames")
     ap.add_argument("--batch", type=int, default=None, help="frames per batched launch (SGM stages); superpixel slots = sequence chunks")
     ap.add_argument("--pipeline", type=int, default=None, help="1 = superpixel pipeline (headline), 0 = naive")
     ap.add_argument("--cpu-sample", type=int, default=6)
@@ -319,70 +341,126 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hbm_peak, peak_src = load_peaks()
 
-    n = args.frames
-    L, R = make_frames(n, rank)
-    hostL = torch.from_numpy(L).pin_memory()
-    hostR = torch.from_numpy(R).pin_memory()
+    from cart_slam_b200.parallel import plan_shards
+
+    sharded = world > 1
+    RESET = 64
+    if sharded:
+        # BASELINE.json configs[4]: one long sequence, sharded at superpixel reset frames
+        total = args.total_frames
+        shards = plan_shards(total, world, RESET)
+        my = shards[rank]
+        n = my.count
+        if rank == 0:
+            make_frames(args.frames, 0)  # generate once, the other ranks read the cache
+        dist.barrier()
+        L, R = make_frames(args.frames, 0)
+        idx = torch.from_numpy((np.arange(my.first_id, my.first_id + n, dtype=np.int64) - 1) % args.frames)
+        hostL = torch.empty((n, H, W, 3), dtype=torch.uint8).pin_memory()
+        hostR = torch.empty((n, H, W, 3), dtype=torch.uint8).pin_memory()
+        torch.index_select(torch.from_numpy(L), 0, idx, out=hostL)
+        torch.index_select(torch.from_numpy(R), 0, idx, out=hostR)
+        max_count = max(sh.count for sh in shards)
+    else:
+        total = n = args.frames
+        shards, my, max_count = None, None, n
+        L, R = make_frames(n, rank)
+        hostL = torch.from_numpy(L).pin_memory()
+        hostR = torch.from_numpy(R).pin_memory()
     devL, devR = hostL.cuda(non_blocking=True), hostR.cuda(non_blocking=True)
-    planes_dev = torch.empty((n, H, W), dtype=torch.uint8, device="cuda")
-    planes_host = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
+    planes_dev = torch.zeros((max_count, H, W), dtype=torch.uint8, device="cuda")  # padded to the largest shard for the gather
+    planes_host = torch.empty((total if rank == 0 else 1, H, W), dtype=torch.uint8).pin_memory()
     torch.cuda.synchronize()
 
     cfg = cb.Config(W, H, max_batch=args.batch, num_disparities=D, min_disparity=MIN_DISP, paths=n_paths, smoothing_radius=2,
                     smoothing_iterations=1, enable_superpixels=args.pipeline == 1, sp_block_size=sp_block)
     ctx = cb.Context(cfg)
-    opts = cb.SequenceOptions(pipeline=args.pipeline, provider=provider, static_params=(1, 30, -3, 1), sp_initial_iterations=24,
-                              sp_iterations=8, sp_reset_iterations=64)
-    gather_buf = None
-    if world > 1 and rank == 0:
-        gather_buf = [torch.empty_like(planes_dev) for _ in range(world)]
 
-    def step_device():
-        ctx.run_sequence_device(opts, devL, devR, planes_out=planes_dev)
-        if world > 1:  # the only collective of the path: the final result gather
-            dist.gather(planes_dev, gather_buf, dst=0)
+    def seq_opts(start_id):
+        return cb.SequenceOptions(pipeline=args.pipeline, provider=provider, static_params=(1, 30, -3, 1), sp_initial_iterations=24,
+                                  sp_iterations=8, sp_reset_iterations=RESET, start_id=start_id)
+    opts = seq_opts(my.first_id if sharded else 1)
+    gather_buf = None
+    if sharded and rank == 0:
+        gather_buf = [torch.empty_like(planes_dev) for _ in range(world)]
+    hist_pad = torch.zeros((max_count, 256), dtype=torch.int32, device="cuda") if sharded else None
+    hist_all = torch.empty((world * max_count, 256), dtype=torch.int32, device="cuda") if sharded else None
+
+    def exchange_parameters(hist):
+        """the only data-path collective besides the result gather: all-gather of the per-frame histograms, then the
+        reference's parameter schedule over the whole sequence on the CPU (every rank computes the same table)"""
+        hist_pad[:n].copy_(torch.from_numpy(hist), non_blocking=False)
+        dist.all_gather_into_tensor(hist_all, hist_pad)
+        ha = hist_all.cpu().numpy().reshape(world, max_count, 256)
+        full = np.concatenate([ha[r, :shards[r].count] for r in range(world)])
+        return cb.sequence_parameters(seq_opts(1), full)[my.frame_slice]
+
+    def compute_device():
+        if not sharded:
+            ctx.run_sequence_device(opts, devL, devR, planes_out=planes_dev)
+            return
+        params = exchange_parameters(ctx.run_sequence_phase1(opts, devL, devR))
+        ctx.run_sequence_phase2(opts, params, planes_out=planes_dev[:n])
+
+    def compute_host():
+        if not sharded:
+            ctx.run_sequence_host(opts, hostL, hostR, planes_out=planes_host)
+            return
+        params = exchange_parameters(ctx.run_sequence_phase1_host(opts, hostL, hostR))
+        ctx.run_sequence_phase2(opts, params, planes_out=planes_dev[:n])
+
+    def gather(to_host):
+        if not sharded:
+            return
+        dist.gather(planes_dev, gather_buf, dst=0)  # the final result gather (padded shards)
+        if to_host and rank == 0:  # the job's result lands in rank 0's host memory
+            o = 0
+            for r in range(world):
+                planes_host[o:o + shards[r].count].copy_(gather_buf[r][:shards[r].count], non_blocking=True)
+                o += shards[r].count
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(compute, to_host):
+        """K steps; returns (total ms, gather ms) on this rank's device clock"""
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        for k in range(args.steps):
+            ev[k][0].record()
+            compute()
+            ev[k][1].record()
+            gather(to_host)
+            ev[k][2].record()
+        barrier()
+        return ev[0][0].elapsed_time(ev[-1][2]), sum(e[1].elapsed_time(e[2]) for e in ev)
+
     for _ in range(args.warmup):
-        step_device()
+        compute_device()
+        gather(False)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms, ms_gather = timed(compute_device, False)
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
-    # end to end through the host-buffer C ABI call
-    for _ in range(1):
-        ctx.run_sequence_host(opts, hostL, hostR, planes_out=planes_host)
+    # end to end through the host-buffer C ABI calls
+    compute_host()
+    gather(True)
     barrier()
     t0 = time.perf_counter()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for _ in range(args.steps):
-        ctx.run_sequence_host(opts, hostL, hostR, planes_out=planes_host)
-    e3.record()
-    barrier()
-    ms_e2e = max(e2.elapsed_time(e3), 0.0)
+    ms_e2e, ms_gather_e2e = timed(compute_host, True)
     wall_e2e = (time.perf_counter() - t0) * 1000.0
-    ms_e2e = max(ms_e2e, wall_e2e)  # the call synchronises internally; take the larger clock
+    ms_e2e = max(ms_e2e, wall_e2e)  # the calls synchronise internally; take the larger clock
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, ms_e2e, ms_gather, ms_gather_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e, ms_gather, ms_gather_e2e = (float(v) for v in t)
 
     # roofline of the dominant kernel: one path-aggregation kernel over a batch of `batch` frames
     roof = None
@@ -400,12 +478,13 @@ def main():
         a1.record()
         torch.cuda.synchronize()
         per_kernel_ms = a0.elapsed_time(a1) / reps / n_paths  # time per path
+        traffic, traffic_note = ncu_traffic_per_launch() if (nb == 64 and args.workload == "kitti") else (None, "only captured for the kitti workload at batch 64")
         alg_bytes = nb * (2 * 4 * W * H + W * H * D)   # read both census images, write one u8 volume
         achieved = alg_bytes / (per_kernel_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": f"aggregate_horizontal_kernel / aggregate_vertical_kernel (mean over the {n_paths} "
                                           f"paths, {nb}-frame batch; opposite directions share a launch, time is per path)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": ncu_traffic_per_launch() if (nb == 64 and args.workload == "kitti") else None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                 "launch_ms": per_kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "compute-limited: every path recomputes the Hamming costs, the POPC pipe (15 lanes/clk/SM "
                         "measured) caps four paths at 69 % of the HBM peak (DESIGN.md section 4)"}
@@ -418,14 +497,26 @@ def main():
         ref_gpu = reference_gpu_kernels()
 
     if rank == 0:
-        total_frames = n * args.steps * world
+        total_frames = total * args.steps
+        if sharded:
+            cfg_workload["workload"] = (
+                f"ONE kitti-shaped synthetic {total}-frame sequence (BASELINE.json configs[4]; frame id i shows distinct frame "
+                f"(i-1) mod {args.frames}) sharded over {world} GPUs at superpixel reset frames, two-pass histogram_peak scheme, "
+                + cfg_workload["workload"].split("per GPU, ", 1)[1])
+            cfg_workload["frames_total"] = total
+            cfg_workload["frames_per_gpu"] = [sh.count for sh in shards]
+            cfg_workload["parallelism"] = f"frame shards x{world}, all-gather of per-frame histograms + final gather of plane labels"
+            cfg_workload["gather_ms_per_step"] = ms_gather / args.steps
+            cfg_workload["compute_ms_per_step"] = (ms - ms_gather) / args.steps
+            cfg_workload["e2e_gather_ms_per_step"] = ms_gather_e2e / args.steps
         out = {
             "metric": METRIC, "value": total_frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": "u8/u16/s16 integer + f64 superpixel costs", "data": "synthetic",
             "config": cfg_workload,
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(2 * n * H * W * 3), "d2h_bytes_per_step": int(n * H * W)},
+                    "h2d_bytes_per_step": int(2 * total * H * W * 3), "d2h_bytes_per_step": int(total * H * W)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "reference_gpu_kernels": ref_gpu,
             "library": cb.version(), "scratch_bytes": ctx.scratch_bytes(),

@@ -1,8 +1,8 @@
 """cart_slam_b200 - Python binding (ctypes) of libcartb200, the B200-native disparity -> planeseg path.
 
 PyTorch is used for device memory and streams only; every computation happens in the hand-written
-sm_100a kernels behind the C ABI declared in include/cartb200.h.  There is no CPU fallback: importing
-this package without the compiled library, or creating a Context without a GPU, fails loudly.
+sm_100a kernels behind the C ABI declared in include/cartb200.h.  There is no CPU fallback: the first
+call into the package without the compiled library, or creating a Context without a GPU, fails loudly.
 """
 from __future__ import annotations
 
@@ -118,7 +118,19 @@ def _load():
     return lib
 
 
-_lib = _load()
+class _LazyLib:
+    """libcartb200.so is mapped on first use, not at import: `import cart_slam_b200.synth` (input generation, also used
+    by the CPU reference arm of bench.py) must not load the CUDA library."""
+
+    _lib = None
+
+    def __getattr__(self, name):
+        if _LazyLib._lib is None:
+            _LazyLib._lib = _load()
+        return getattr(_LazyLib._lib, name)
+
+
+_lib = _LazyLib()
 
 EXPORTED_SYMBOLS = [
     "cartb200_default_config", "cartb200_create", "cartb200_last_create_error", "cartb200_destroy", "cartb200_last_error", "cartb200_version",
