@@ -219,6 +219,37 @@ def reference_gpu_kernels():
         return {"error": str(e)}
 
 
+def module_layer_arm(L, R, n_frames: int = 96):
+    """The drop-in path as a maintainer gets it on day one: the C++ module layer (SystemModule::run per frame and module,
+    DataElement hand-off, kitti-planeseg.json's module list with the bench's iteration counts), one frame per C-ABI call,
+    up to CARTSLAM_CONCURRENT_RUN_LIMIT frames in flight like the reference's main loop (cartslam.cpp:255-302).  Host
+    frames in, plane labels out (host); wall clock."""
+    try:
+        from cart_slam_b200 import host as cart_host
+
+        modules = [
+            {"type": "superpixels", "initial_iterations": 24, "iterations": 8, "block_size": 12, "reset_iterations": 64},
+            {"type": "optflow"},
+            {"type": "disparity", "min_disparity": MIN_DISP, "num_disparities": D, "smoothing_radius": 2, "smoothing_iterations": 1},
+            {"type": "disparity_derivative"},
+            {"type": "superpixel_disparity_planeseg", "parameter_provider": {"type": "histogram_peak"}},
+            {"type": "bev_planeseg_visualization"},
+        ]
+        n = min(n_frames, L.shape[0])
+        cart_host.run_config(modules, L[:8], R[:8], skip_out_of_scope=True, sequential=False)  # warm-up (contexts, allocator)
+        res = {}
+        for name, seq in (("in_flight_12", False), ("sequential", True)):
+            t0 = time.perf_counter()
+            cart_host.run_config(modules, L[:n], R[:n], skip_out_of_scope=True, sequential=seq)
+            res[name] = n / (time.perf_counter() - t0)
+        return {"value": res["in_flight_12"], "unit": UNIT, "sequential_value": res["sequential"], "frames": n,
+                "what": "cartb200_host_run_config: per-frame SystemModule::run calls (n = 1 per C-ABI call, one context per module, "
+                        "a stream created and synchronised per call as the reference does), kitti-planeseg.json module list minus "
+                        "out-of-scope modules, host frames in / host planes out, wall clock; value = up to 12 frames in flight"}
+    except Exception as e:  # reported, never fatal
+        return {"error": str(e)}
+
+
 def cpu_arm(n_sample: int, L, R):
     """OpenCV CPU StereoSGBM + scalar oracle planeseg half.  One independent frame chain per host core (frame chunks
     of a sequence are independent, so this is how a CPU implementation shards them): every worker thread runs the same
@@ -491,10 +522,12 @@ def main():
 
     cpu = None
     ref_gpu = None
+    module_layer = None
     if rank == 0 and world == 1 and args.workload == "kitti":  # the other workloads are recorded without CPU arms
         v, threads, sample = cpu_arm(args.cpu_sample, L, R)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
         ref_gpu = reference_gpu_kernels()
+        module_layer = module_layer_arm(L, R)
 
     if rank == 0:
         total_frames = total * args.steps
@@ -518,7 +551,7 @@ def main():
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(2 * total * H * W * 3), "d2h_bytes_per_step": int(total * H * W)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "reference_gpu_kernels": ref_gpu,
+            "reference_gpu_kernels": ref_gpu, "module_layer": module_layer,
             "library": cb.version(), "scratch_bytes": ctx.scratch_bytes(),
         }
         sys.stdout.flush()

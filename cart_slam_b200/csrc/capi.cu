@@ -103,8 +103,21 @@ int checkSgm(cartb200_ctx* c) {
     return CARTB200_OK;
 }
 
+// every buffer and kernel attribute of a context belongs to the device it was created on
+int checkDevice(cartb200_ctx* c) {
+    if (!c) return CARTB200_E_ARG;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != c->device) {
+        c->err = "the context was created on CUDA device " + std::to_string(c->device) + " but device " + std::to_string(dev) +
+                 " is current: call cudaSetDevice first (one context per device)";
+        return CARTB200_E_ARG;
+    }
+    return CARTB200_OK;
+}
+
 int checkBatch(cartb200_ctx* c, int n) {
     if (!c) return CARTB200_E_ARG;
+    if (int rc = checkDevice(c)) return rc;
     if (n < 1 || n > c->B) {
         c->err = "batch size " + std::to_string(n) + " outside 1.." + std::to_string(c->B);
         return CARTB200_E_ARG;
@@ -176,6 +189,11 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
     if (cfg->width < 16 || cfg->height < 8 || cfg->max_batch < 1) {
         c->err = "invalid size / batch";
         return fail(CARTB200_E_ARG);
+    }
+    if (cfg->width > 8192 || cfg->height > 8192) {
+        // coordinates travel in 13 + 13 bits and 32 warp-merged x^2 / y^2 terms are summed in 32-bit integers
+        c->err = "images larger than 8192 x 8192 are not supported";
+        return fail(CARTB200_E_UNSUPPORTED);
     }
     if (cfg->num_disparities != 64 && cfg->num_disparities != 128 && cfg->num_disparities != 256) {
         c->err = "num_disparities must be 64, 128 or 256 (cv::cuda::StereoSGM restriction)";
@@ -264,11 +282,13 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
             c->err = "superpixel count must stay below 16384 (OUT_OF_BOUNDS marker, contourrelaxation.cu:21)";
             return fail(CARTB200_E_UNSUPPORTED);
         }
+        if ((rc = devAlloc(c, &c->votes, B * (size_t)c->maxLabels * 4 * sizeof(uint32_t)))) return fail(rc);
+    }
+    if (cfg->enable_superpixels == 1) {  // 2 = only the vote table of the superpixel plane segmentation
         c->spLabelPitch = alignUp(W * 2, 128);
         if ((rc = devAlloc(c, &c->spLabels, B * 2 * H * c->spLabelPitch))) return fail(rc);  // two planes per slot
         if ((rc = devAlloc(c, &c->spYcc, B * H * W * 4))) return fail(rc);
         if ((rc = devAlloc(c, &c->spStats, B * (size_t)(c->maxLabels + 1) * 40 * sizeof(double)))) return fail(rc);
-        if ((rc = devAlloc(c, &c->votes, B * (size_t)c->maxLabels * 4 * sizeof(uint32_t)))) return fail(rc);
         {
             std::vector<int> tileMap;
             std::vector<uint32_t> tab;
@@ -785,6 +805,7 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
         if (c) c->err = "run_sequence: bad arguments";
         return CARTB200_E_ARG;
     }
+    if (int rcDev = checkDevice(c)) return rcDev;
     if (o->pipeline != 0 && o->pipeline != 1) {
         c->err = "run_sequence: unknown pipeline";
         return CARTB200_E_ARG;

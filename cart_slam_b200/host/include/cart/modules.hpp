@@ -45,7 +45,8 @@ typedef uint16_t label_t;
 // RAII handle on a cartb200 context; throws std::runtime_error with cartb200_last_error on failure.
 class Kernels {
    public:
-    Kernels(Size size, bool sgm, bool superpixels, int minDisparity = 4, int numDisparities = 256, int smoothingRadius = -1,
+    // superpixels: 0 = none, 1 = full relaxation scratch, 2 = only the vote table of the superpixel plane segmentation
+    Kernels(Size size, bool sgm, int superpixels, int minDisparity = 4, int numDisparities = 256, int smoothingRadius = -1,
             int smoothingIterations = 5, int spBlockSize = 12, double direct = 0.5, double diagonal = 0.5 / std::sqrt(2.0),
             double wCompact = 0.1, double progressive = 0.0, double wImage = 1.5, double wDisparity = 1.0);
     ~Kernels();

@@ -5,7 +5,10 @@
 // cv::imread is replaced by a small PNG reader (8-bit gray / RGB / RGBA / palette, non-interlaced; zlib inflate),
 // which returns BGR like IMREAD_COLOR does.  The ZED source needs the proprietary ZED SDK: out of scope.
 #pragma once
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cart/core.hpp"
@@ -19,10 +22,16 @@ void readPngBgr(const std::string& path, std::vector<uint8_t>& bgr, int& width, 
 }  // namespace util
 
 namespace sources {
+// Frames are decoded ahead of the consumer by a small pool of threads (PNG inflate costs ~10 ms per KITTI image and
+// core) into a ring of PINNED host slots; getNext() uploads the ready slot with two asynchronous copies on the caller's
+// stream.  CARTB200_KITTI_DECODE_THREADS / CARTB200_KITTI_RING override the pool size (default min(cores, 16)) and the
+// ring depth (default 2 x threads).  The reference reads and uploads one frame at a time inside getNextInternal
+// (kitti.cpp:155-186).
 class KITTIDataSource : public DataSource {
    public:
     KITTIDataSource(std::string basePath, int sequence, Size imageSize = Size(0, 0));
     explicit KITTIDataSource(std::string path, Size imageSize = Size(0, 0));
+    ~KITTIDataSource() override;
     bool isNextReady() override;
     bool isFinished() override;
     DataElementType getProvidedType() override { return STEREO; }
@@ -33,9 +42,25 @@ class KITTIDataSource : public DataSource {
    private:
     void init();
     std::string framePath(int cam, int frame) const;
+    void startPrefetch();
+    void prefetchWorker();
     std::string path;
     int currentFrame = 0;
     std::vector<uint8_t> bufL, bufR;
+    // prefetch ring: frame f lives in slot f % ring.size()
+    struct Slot {
+        uint8_t* left = nullptr;   // pinned, W*H*3 each
+        uint8_t* right = nullptr;
+        int frame = -1;
+        enum State { FREE, LOADING, READY, FAILED, END } state = FREE;
+        std::string error;
+    };
+    std::vector<Slot> ring;
+    std::vector<std::thread> workers;
+    std::mutex ringMutex;
+    std::condition_variable ringCv;
+    int nextToLoad = 0;
+    bool stopPrefetch = false, sawEnd = false;
 };
 }  // namespace sources
 

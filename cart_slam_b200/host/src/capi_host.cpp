@@ -133,18 +133,28 @@ int cartb200_host_run_source(const char* source_json, const char* modules_json, 
         auto system = std::make_shared<System>(source, workers);
         config::applyModuleConfigText(modules_json, system, skip_out_of_scope != 0);
         const size_t px = (size_t)size.width * size.height;
-        int done = 0;
-        while (done < max_frames && !source->isFinished()) {
-            system->run().get();  // in id order
-            ++done;
-            auto run = system->getRunById((uint32_t)done);
+        // up to CARTSLAM_CONCURRENT_RUN_LIMIT frames in flight like the reference's main loop; the modules keep id order
+        int done = 0, started = 0;
+        std::deque<std::pair<uint32_t, std::future<void>>> inflight;
+        auto collect = [&]() {
+            const uint32_t fid = inflight.front().first;
+            inflight.front().second.get();
+            inflight.pop_front();
+            auto run = system->getRunById(fid);
             if (planes_out && run->hasData(CARTSLAM_KEY_PLANES))
-                run->getData<image_t>(CARTSLAM_KEY_PLANES)->download(planes_out + px * (done - 1), (size_t)size.width);
+                run->getData<image_t>(CARTSLAM_KEY_PLANES)->download(planes_out + px * (fid - 1), (size_t)size.width);
             if (disparity_out && run->hasData(CARTSLAM_KEY_DISPARITY))
-                run->getData<image_t>(CARTSLAM_KEY_DISPARITY)->download(disparity_out + px * (done - 1), (size_t)size.width * 2);
+                run->getData<image_t>(CARTSLAM_KEY_DISPARITY)->download(disparity_out + px * (fid - 1), (size_t)size.width * 2);
             if (depth_out && run->hasData(CARTSLAM_KEY_DEPTH))
-                run->getData<image_t>(CARTSLAM_KEY_DEPTH)->download(depth_out + px * 3 * (done - 1), (size_t)size.width * 12);
+                run->getData<image_t>(CARTSLAM_KEY_DEPTH)->download(depth_out + px * 3 * (fid - 1), (size_t)size.width * 12);
+            ++done;
+        };
+        while (started < max_frames && !source->isFinished()) {
+            auto f = system->run();
+            inflight.emplace_back((uint32_t)++started, std::move(f));
+            if (inflight.size() >= CARTSLAM_CONCURRENT_RUN_LIMIT) collect();
         }
+        while (!inflight.empty()) collect();
         return done;
     } catch (const std::exception& e) {
         g_error.clear();

@@ -25,7 +25,7 @@ struct StreamGuard {  // the reference creates and synchronises one stream per m
 };
 }  // namespace
 
-Kernels::Kernels(Size size, bool sgm, bool superpixels, int minDisparity, int numDisparities, int smoothingRadius,
+Kernels::Kernels(Size size, bool sgm, int superpixels, int minDisparity, int numDisparities, int smoothingRadius,
                  int smoothingIterations, int spBlockSize, double direct, double diagonal, double wCompact, double progressive,
                  double wImage, double wDisparity) {
     cartb200_config cfg;
@@ -60,7 +60,7 @@ ImageDisparityModule::ImageDisparityModule(const Size imageRes, int minDisparity
     : SyncWrapperSystemModule("ImageDisparity") {
     (void)blockSize;  // setBlockSize is a no-op for cv::cuda::StereoSGM
     providesData.push_back(CARTSLAM_KEY_DISPARITY);
-    kernels.reset(new Kernels(imageRes, true, false, minDisparity, numDisparities, smoothingRadius, smoothingIterations));
+    kernels.reset(new Kernels(imageRes, true, 0, minDisparity, numDisparities, smoothingRadius, smoothingIterations));
 }
 
 system_data_t ImageDisparityModule::runInternal(System&, SystemRunData& data) {
@@ -95,7 +95,7 @@ system_data_t ImageDisparityDerivativeModule::runInternal(System&, SystemRunData
     {
         static std::mutex createMutex;
         std::lock_guard<std::mutex> lock(createMutex);
-        if (!kernels) kernels.reset(new Kernels(disparity->size(), false, false));
+        if (!kernels) kernels.reset(new Kernels(disparity->size(), false, 0));
     }
     {
         std::lock_guard<std::mutex> lock(kernels->mutex);
@@ -123,7 +123,7 @@ system_data_t DepthModule::runInternal(System& system, SystemRunData& data) {
     {
         static std::mutex createMutex;
         std::lock_guard<std::mutex> lock(createMutex);
-        if (!kernels) kernels.reset(new Kernels(disparity->size(), false, false));
+        if (!kernels) kernels.reset(new Kernels(disparity->size(), false, 0));
     }
     {
         std::lock_guard<std::mutex> lock(kernels->mutex);
@@ -154,7 +154,7 @@ SuperPixelModule::SuperPixelModule(const Size imageRes, const unsigned int initi
     providesData.push_back(CARTSLAM_KEY_SUPERPIXELS);
     providesData.push_back(CARTSLAM_KEY_SUPERPIXELS_MAX_LABEL);
     // context creation performs createBlockInitialization on its label slot (superpixels.cu:56-58)
-    kernels.reset(new Kernels(imageRes, false, true, 4, 256, -1, 5, (int)blockSize, directCliqueCost, diagonalCliqueCost, compactnessWeight,
+    kernels.reset(new Kernels(imageRes, false, 1, 4, 256, -1, 5, (int)blockSize, directCliqueCost, diagonalCliqueCost, compactnessWeight,
                               progressiveCompactnessCost, imageWeight, disparityWeight));
     int ml = 0;
     kernels->check(cartb200_superpixels_reset(kernels->get(), 1, nullptr, &ml, nullptr), "SuperPixelModule");
@@ -291,7 +291,7 @@ system_data_t DisparityPlaneSegmentationModule::runInternal(System& system, Syst
     {
         static std::mutex createMutex;
         std::lock_guard<std::mutex> lock(createMutex);
-        if (!kernels) kernels.reset(new Kernels(disparity->size(), false, false));
+        if (!kernels) kernels.reset(new Kernels(disparity->size(), false, 0));
     }
     std::lock_guard<std::mutex> klock(kernels->mutex);  // also orders the running total by arrival
     kernels->check(cartb200_naive_derivative(kernels->get(), 1, disparity->as<int16_t>(), disparity->pitch, 0, derivatives.as<int16_t>(),
@@ -383,7 +383,7 @@ system_data_t SuperPixelDisparityPlaneSegmentationModule::runInternal(System& sy
         if (!kernels) {
             int bs = 1;
             while ((long)((derivatives->cols + bs - 1) / bs) * ((derivatives->rows + bs - 1) / bs) > 16383) ++bs;
-            kernels.reset(new Kernels(derivatives->size(), false, true, 4, 256, -1, 5, bs));
+            kernels.reset(new Kernels(derivatives->size(), false, 2, 4, 256, -1, 5, bs));  // vote table only
         }
     }
     if (useTemporalSmoothing) {  // sp_planeseg.cu:256-345

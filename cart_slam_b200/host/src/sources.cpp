@@ -1,6 +1,7 @@
 // KITTI odometry data source + PNG reader (see cart/sources.hpp for the reference files this follows).
 #include "cart/sources.hpp"
 
+#include <cuda_runtime.h>
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -32,9 +33,12 @@ int paeth(int a, int b, int c) {
 }  // namespace
 
 void readPngBgr(const std::string& path, std::vector<uint8_t>& bgr, int& width, int& height) {
-    std::ifstream f(path, std::ios::binary);
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
     if (!f.is_open()) throw std::runtime_error("Failed to open image " + path + ": " + strerror(errno));
-    std::vector<uint8_t> file((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    const std::streamsize fileSize = f.tellg();
+    std::vector<uint8_t> file(fileSize > 0 ? (size_t)fileSize : 0);
+    f.seekg(0);
+    if (!file.empty() && !f.read(reinterpret_cast<char*>(file.data()), fileSize)) throw std::runtime_error("Failed to read image " + path);
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     if (file.size() < 8 + 25 || std::memcmp(file.data(), sig, 8) != 0) throw std::runtime_error(path + ": not a PNG file");
     int bitDepth = 0, colorType = 0, interlace = 0;
@@ -80,46 +84,62 @@ void readPngBgr(const std::string& path, std::vector<uint8_t>& bgr, int& width, 
     uLongf rawLen = (uLongf)raw.size();
     if (uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size()) != Z_OK || rawLen != raw.size())
         throw std::runtime_error(path + ": PNG inflate failed");
-    // undo the scanline filters in place
-    std::vector<uint8_t> prevRow(stride, 0);
+    // undo the scanline filters in place, one specialised loop per filter type (the per-byte dispatch of a generic
+    // loop costs more than the inflate)
     bgr.resize((size_t)width * height * 3);
+    const uint8_t* prev = nullptr;  // previous (unfiltered) row; nullptr = the all-zero row above the image
     for (int y = 0; y < height; ++y) {
         uint8_t* row = &raw[(stride + 1) * (size_t)y];
         const int filter = row[0];
         uint8_t* px = row + 1;
-        for (size_t i = 0; i < stride; ++i) {
-            const int a = i >= (size_t)ch ? px[i - ch] : 0, b = prevRow[i], c = i >= (size_t)ch ? prevRow[i - ch] : 0;
-            int v = px[i];
-            switch (filter) {
-                case 0: break;
-                case 1: v += a; break;
-                case 2: v += b; break;
-                case 3: v += (a + b) >> 1; break;
-                case 4: v += paeth(a, b, c); break;
-                default: throw std::runtime_error(path + ": bad PNG filter");
-            }
-            px[i] = (uint8_t)v;
+        const size_t bpp = (size_t)ch;
+        switch (filter) {
+            case 0: break;
+            case 1:
+                for (size_t i = bpp; i < stride; ++i) px[i] = (uint8_t)(px[i] + px[i - bpp]);
+                break;
+            case 2:
+                if (prev)
+                    for (size_t i = 0; i < stride; ++i) px[i] = (uint8_t)(px[i] + prev[i]);
+                break;
+            case 3:
+                for (size_t i = 0; i < bpp && i < stride; ++i) px[i] = (uint8_t)(px[i] + ((prev ? prev[i] : 0) >> 1));
+                for (size_t i = bpp; i < stride; ++i) px[i] = (uint8_t)(px[i] + ((px[i - bpp] + (prev ? prev[i] : 0)) >> 1));
+                break;
+            case 4:
+                for (size_t i = 0; i < bpp && i < stride; ++i) px[i] = (uint8_t)(px[i] + (prev ? prev[i] : 0));  // paeth(0, b, 0) = b
+                if (prev) {
+                    for (size_t i = bpp; i < stride; ++i) px[i] = (uint8_t)(px[i] + paeth(px[i - bpp], prev[i], prev[i - bpp]));
+                } else {
+                    for (size_t i = bpp; i < stride; ++i) px[i] = (uint8_t)(px[i] + px[i - bpp]);  // paeth(a, 0, 0) = a
+                }
+                break;
+            default: throw std::runtime_error(path + ": bad PNG filter");
         }
-        std::memcpy(prevRow.data(), px, stride);
+        prev = px;
         uint8_t* out = &bgr[(size_t)y * width * 3];
-        for (int x = 0; x < width; ++x) {
-            uint8_t r, g, bl;
-            if (colorType == 0 || colorType == 4) {
-                r = g = bl = px[(size_t)x * ch];
-            } else if (colorType == 3) {
+        if (colorType == 2) {  // RGB -> BGR (cv::imread(IMREAD_COLOR) returns BGR)
+            for (int x = 0; x < width; ++x) {
+                out[3 * x] = px[3 * x + 2];
+                out[3 * x + 1] = px[3 * x + 1];
+                out[3 * x + 2] = px[3 * x];
+            }
+        } else if (colorType == 6) {  // RGBA: alpha dropped
+            for (int x = 0; x < width; ++x) {
+                out[3 * x] = px[4 * x + 2];
+                out[3 * x + 1] = px[4 * x + 1];
+                out[3 * x + 2] = px[4 * x];
+            }
+        } else if (colorType == 3) {
+            for (int x = 0; x < width; ++x) {
                 const size_t k = (size_t)px[x] * 3;
                 if (k + 2 >= palette.size()) throw std::runtime_error(path + ": palette index out of range");
-                r = palette[k];
-                g = palette[k + 1];
-                bl = palette[k + 2];
-            } else {
-                r = px[(size_t)x * ch];
-                g = px[(size_t)x * ch + 1];
-                bl = px[(size_t)x * ch + 2];
+                out[3 * x] = palette[k + 2];
+                out[3 * x + 1] = palette[k + 1];
+                out[3 * x + 2] = palette[k];
             }
-            out[3 * x] = bl;  // cv::imread(IMREAD_COLOR) returns BGR and drops alpha
-            out[3 * x + 1] = g;
-            out[3 * x + 2] = r;
+        } else {  // gray (+ alpha): replicated
+            for (int x = 0; x < width; ++x) out[3 * x] = out[3 * x + 1] = out[3 * x + 2] = px[(size_t)x * ch];
         }
     }
 }
@@ -229,17 +249,99 @@ bool KITTIDataSource::isNextReady() {
 
 bool KITTIDataSource::isFinished() { return !isNextReady(); }
 
+KITTIDataSource::~KITTIDataSource() {
+    {
+        std::lock_guard<std::mutex> lock(ringMutex);
+        stopPrefetch = true;
+    }
+    ringCv.notify_all();
+    for (auto& w : workers) w.join();
+    for (auto& s : ring) {
+        cudaFreeHost(s.left);
+        cudaFreeHost(s.right);
+    }
+}
+
+void KITTIDataSource::startPrefetch() {
+    unsigned threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("CARTB200_KITTI_DECODE_THREADS"))
+        if (atoi(e) > 0) threads = (unsigned)atoi(e);
+    size_t depth = 2 * (size_t)threads;
+    if (const char* e = getenv("CARTB200_KITTI_RING"))
+        if (atoi(e) > 0) depth = (size_t)atoi(e);
+    const size_t bytes = (size_t)imageSize.width * imageSize.height * 3;
+    ring.resize(depth);
+    for (auto& s : ring)
+        if (cudaMallocHost((void**)&s.left, bytes) != cudaSuccess || cudaMallocHost((void**)&s.right, bytes) != cudaSuccess)
+            throw std::runtime_error("KITTIDataSource: cudaMallocHost of the frame ring failed");
+    for (unsigned i = 0; i < threads; ++i) workers.emplace_back([this] { prefetchWorker(); });
+}
+
+// Each worker claims the next frame whose slot is free, decodes both images into the slot and marks it ready.
+void KITTIDataSource::prefetchWorker() {
+    std::vector<uint8_t> tmp;
+    const size_t bytes = (size_t)imageSize.width * imageSize.height * 3;
+    for (;;) {
+        int frame;
+        Slot* slot;
+        {
+            std::unique_lock<std::mutex> lock(ringMutex);
+            ringCv.wait(lock, [this] { return stopPrefetch || (!sawEnd && ring[(size_t)nextToLoad % ring.size()].state == Slot::FREE); });
+            if (stopPrefetch) return;
+            frame = nextToLoad++;
+            slot = &ring[(size_t)frame % ring.size()];
+            slot->state = Slot::LOADING;
+            slot->frame = frame;
+        }
+        Slot::State result = Slot::READY;
+        std::string error;
+        struct stat st;
+        if (stat(framePath(kLeftCam, frame).c_str(), &st) != 0) {
+            result = Slot::END;
+        } else {
+            try {
+                int w = 0, h = 0;
+                for (int cam = 0; cam < 2; ++cam) {
+                    util::readPngBgr(framePath(cam ? kRightCam : kLeftCam, frame), tmp, w, h);
+                    if (w != imageSize.width || h != imageSize.height)
+                        throw std::runtime_error("KITTIDataSource: frame " + std::to_string(frame) + " has a different size");
+                    std::memcpy(cam ? slot->right : slot->left, tmp.data(), bytes);
+                }
+            } catch (const std::exception& e) {
+                result = Slot::FAILED;
+                error = e.what();
+            }
+        }
+        {
+            std::lock_guard<std::mutex> lock(ringMutex);
+            slot->state = result;
+            slot->error = error;
+            if (result == Slot::END) sawEnd = true;  // frames are consecutive: nothing beyond the first gap is read
+        }
+        ringCv.notify_all();
+    }
+}
+
 std::shared_ptr<DataElement> KITTIDataSource::getNextInternal(void* stream) {
-    int wl = 0, hl = 0, wr = 0, hr = 0;
-    util::readPngBgr(framePath(kLeftCam, currentFrame), bufL, wl, hl);
-    util::readPngBgr(framePath(kRightCam, currentFrame), bufR, wr, hr);
-    if (wl != imageSize.width || hl != imageSize.height || wr != wl || hr != hl)
-        throw std::runtime_error("KITTIDataSource: frame " + std::to_string(currentFrame) + " has a different size");
-    ++currentFrame;
+    if (ring.empty()) startPrefetch();
+    Slot* slot = &ring[(size_t)currentFrame % ring.size()];
+    {
+        std::unique_lock<std::mutex> lock(ringMutex);
+        ringCv.wait(lock, [&] { return slot->frame == currentFrame && slot->state != Slot::LOADING && slot->state != Slot::FREE; });
+        if (slot->state == Slot::END) throw std::runtime_error("KITTIDataSource: frame " + std::to_string(currentFrame) + " does not exist");
+        if (slot->state == Slot::FAILED) throw std::runtime_error(slot->error);
+    }
     image_t l(imageSize.height, imageSize.width, IMG_8UC3), r(imageSize.height, imageSize.width, IMG_8UC3);
-    l.upload(bufL.data(), (size_t)imageSize.width * 3, stream);
-    r.upload(bufR.data(), (size_t)imageSize.width * 3, stream);
-    syncStream(stream);  // bufL / bufR are reused by the next frame
+    l.upload(slot->left, (size_t)imageSize.width * 3, stream);  // pinned source: truly asynchronous copies
+    r.upload(slot->right, (size_t)imageSize.width * 3, stream);
+    syncStream(stream);  // the slot goes back to the decoders
+    {
+        std::lock_guard<std::mutex> lock(ringMutex);
+        slot->state = Slot::FREE;
+        slot->frame = -1;
+    }
+    ringCv.notify_all();
+    ++currentFrame;
     return std::make_shared<StereoDataElement>(l, r);
 }
 }  // namespace sources

@@ -56,7 +56,8 @@ typedef struct cartb200_config {
     int paths;            /* 4 (MODE_HH4) or 8 (MODE_HH) */
     int smoothing_radius; /* <= 0: no interpolation */
     int smoothing_iterations;
-    /* superpixels (enable_superpixels = 0 skips allocating their scratch) */
+    /* superpixels: 0 = no scratch; 1 = everything; 2 = only the per-label vote table cartb200_sp_planeseg* need, sized
+     * for the label count sp_block_size implies (a module that consumes labels produced elsewhere) */
     int enable_superpixels;
     int sp_block_size; /* 12 */
     double sp_direct_clique_cost, sp_diagonal_clique_cost;

@@ -13,11 +13,34 @@ import bench  # noqa: E402
 
 
 def test_ncu_traffic_matches_the_algorithmic_bytes_of_one_path():
-    t = bench.ncu_traffic_per_launch()
-    assert t is not None, "profiles/ holds no ncu summary of the aggregation kernels"
+    """roofline.traffic comes from the newest committed `ncu --set full` summary of the aggregation kernels - and only
+    while that summary was captured from the csrc/sgm.cu that is in the tree (hash stamped by tools/ncu_raw_summary.py)."""
+    t, note = bench.ncu_traffic_per_launch()
+    assert note
+    assert t is not None, f"the committed aggregation summary does not match the kernels in the tree: {note}"
     W, H, D, B = 1242, 375, 128, 64
     algorithmic = B * (W * H * D + 2 * 4 * W * H)  # SURVEY 8(d): read both census images, write one u8 volume
     assert abs(t / algorithmic - 1.0) < 0.03, (t, algorithmic)  # no wasted re-reads
+
+
+def test_a_stale_ncu_summary_is_not_reported(tmp_path, monkeypatch):
+    import shutil
+    root = tmp_path / "repo"
+    (root / "profiles").mkdir(parents=True)
+    (root / "cart_slam_b200" / "csrc").mkdir(parents=True)
+    shutil.copy(os.path.join(ROOT, "cart_slam_b200", "csrc", "sgm.cu"), root / "cart_slam_b200" / "csrc" / "sgm.cu")
+    launch = {"kernel": "aggregate_vertical_kernel", "launch__grid_size []": 10.0, "dram__bytes_read.sum [Mbyte]": 100.0,
+              "dram__bytes_write.sum [Gbyte]": 3.9}
+    monkeypatch.setattr(bench, "ROOT", str(root))
+    json.dump({"source_sha16": "0" * 16, "launches": [launch]}, open(root / "profiles" / "r09_ncu_aggregate_batch64.json", "w"))
+    t, note = bench.ncu_traffic_per_launch()
+    assert t is None and "stale" in note
+    json.dump({"launches": [launch]}, open(root / "profiles" / "r09_ncu_aggregate_batch64.json", "w"))
+    assert bench.ncu_traffic_per_launch()[0] is None
+    json.dump({"source_sha16": bench._sha16(str(root / "cart_slam_b200" / "csrc" / "sgm.cu")), "launches": [launch]},
+              open(root / "profiles" / "r09_ncu_aggregate_batch64.json", "w"))
+    t, note = bench.ncu_traffic_per_launch()
+    assert t == pytest.approx(4.0e9)
 
 
 def test_workloads_are_the_baseline_configs():

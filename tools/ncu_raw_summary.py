@@ -28,7 +28,13 @@ def main():
     for d in out:
         print(json.dumps(d))
     if len(sys.argv) > 2:
-        json.dump({"launches": out}, open(sys.argv[2], "w"), indent=1)
+        import hashlib
+        import os
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sha = {f: hashlib.sha256(open(os.path.join(root, "cart_slam_b200", "csrc", f), "rb").read()).hexdigest()[:16]
+               for f in ("sgm.cu", "superpixels.cu", "post_stages.cu")}
+        # bench.py reports roofline.traffic from an aggregation summary only while csrc/sgm.cu still has this hash
+        json.dump({"source_sha16": sha["sgm.cu"], "sources_sha16": sha, "launches": out}, open(sys.argv[2], "w"), indent=1)
 
 
 main()
