@@ -63,6 +63,7 @@ class DeviceImage {
    private:
     struct Buf {
         void* p = nullptr;
+        size_t widthBytes = 0, rows = 0, pitch = 0;  // the pool key and what goes back to it
         ~Buf();
     };
     std::shared_ptr<Buf> buf;
@@ -177,6 +178,7 @@ class MemoryDataSource : public DataSource {
    public:
     MemoryDataSource(Size size, int nFrames, const uint8_t* leftBgr, const uint8_t* rightBgr)
         : DataSource(size), n(nFrames), left(leftBgr), right(rightBgr) {}
+    ~MemoryDataSource() override;
     bool isNextReady() override { return next < n; }
     bool isFinished() override { return next >= n; }
     DataElementType getProvidedType() override { return STEREO; }
@@ -187,6 +189,10 @@ class MemoryDataSource : public DataSource {
    private:
     int n, next = 0;
     const uint8_t *left, *right;
+    // frames are staged through a pinned buffer and uploaded on a private non-blocking stream: a copy from pageable
+    // memory on the legacy default stream serialises against everything else that is in flight
+    uint8_t* staging = nullptr;
+    void* copyStream = nullptr;
 };
 
 // ---- modules ---------------------------------------------------------------------------------------

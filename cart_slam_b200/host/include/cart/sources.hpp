@@ -61,6 +61,7 @@ class KITTIDataSource : public DataSource {
     std::condition_variable ringCv;
     int nextToLoad = 0;
     bool stopPrefetch = false, sawEnd = false;
+    void* copyStream = nullptr;
 };
 }  // namespace sources
 

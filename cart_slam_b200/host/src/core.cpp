@@ -9,6 +9,9 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
 
 namespace cart {
 
@@ -38,13 +41,62 @@ size_t imageElemBytes(ImageType t) {
     return 1;
 }
 
+// Device images are recycled through a size-keyed pool: a frame allocates about ten of them (inputs, disparity,
+// derivatives, labels, planes ...), and cudaFree synchronises the whole device - with cudaMallocPitch / cudaFree per
+// image (what cv::cuda::GpuMat does without a BufferPool) the module layer spent ~10 ms of host time per frame on them.
+// Buffers return to the pool when the last DeviceImage that shares them goes away; the pool is capped
+// (CARTB200_IMAGE_POOL_MB, default 4096) and anything beyond the cap is really freed.
+namespace {
+struct ImagePool {
+    std::mutex m;
+    std::map<std::pair<size_t, size_t>, std::vector<std::pair<void*, size_t>>> free;  // (width bytes, rows) -> (ptr, pitch)
+    size_t bytes = 0, cap = 4096ull << 20;
+    ImagePool() {
+        if (const char* e = std::getenv("CARTB200_IMAGE_POOL_MB")) cap = (size_t)std::max(0, std::atoi(e)) << 20;
+    }
+    ~ImagePool() {  // process exit: the driver may already be gone, ignore errors
+        for (auto& kv : free)
+            for (auto& b : kv.second) cudaFree(b.first);
+    }
+    bool take(size_t widthBytes, size_t rows, void** p, size_t* pitch) {
+        std::lock_guard<std::mutex> lock(m);
+        auto it = free.find({widthBytes, rows});
+        if (it == free.end() || it->second.empty()) return false;
+        *p = it->second.back().first;
+        *pitch = it->second.back().second;
+        it->second.pop_back();
+        bytes -= *pitch * rows;
+        return true;
+    }
+    void give(size_t widthBytes, size_t rows, void* p, size_t pitch) {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            if (bytes + pitch * rows <= cap) {
+                free[{widthBytes, rows}].emplace_back(p, pitch);
+                bytes += pitch * rows;
+                return;
+            }
+        }
+        cudaFree(p);
+    }
+};
+ImagePool& imagePool() {
+    static ImagePool* pool = new ImagePool();  // leaked on purpose: images may outlive static destruction order
+    return *pool;
+}
+}  // namespace
+
 DeviceImage::Buf::~Buf() {
-    if (p) cudaFree(p);
+    if (p) imagePool().give(widthBytes, rows, p, pitch);
 }
 
 DeviceImage::DeviceImage(int rows_, int cols_, ImageType type_) : rows(rows_), cols(cols_), type(type_) {
     buf = std::make_shared<Buf>();
-    cudaCheck(cudaMallocPitch(&buf->p, &pitch, (size_t)cols * imageElemBytes(type), rows), "cudaMallocPitch");
+    buf->widthBytes = (size_t)cols * imageElemBytes(type);
+    buf->rows = (size_t)rows;
+    if (!imagePool().take(buf->widthBytes, buf->rows, &buf->p, &pitch))
+        cudaCheck(cudaMallocPitch(&buf->p, &pitch, buf->widthBytes, rows), "cudaMallocPitch");
+    buf->pitch = pitch;
 }
 
 void DeviceImage::upload(const void* host, size_t hostPitch, void* stream) {
@@ -166,12 +218,25 @@ std::shared_ptr<DataElement> DataSource::getNext(void* stream) {
     return element;
 }
 
-std::shared_ptr<DataElement> MemoryDataSource::getNextInternal(void* stream) {
+MemoryDataSource::~MemoryDataSource() {
+    if (staging) cudaFreeHost(staging);
+    if (copyStream) cudaStreamDestroy((cudaStream_t)copyStream);
+}
+
+std::shared_ptr<DataElement> MemoryDataSource::getNextInternal(void*) {
     const size_t frame = (size_t)imageSize.width * imageSize.height * 3;
+    if (!staging) {
+        cudaCheck(cudaMallocHost((void**)&staging, 2 * frame), "cudaMallocHost");
+        cudaStream_t s = nullptr;
+        cudaCheck(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+        copyStream = s;
+    }
     image_t l(imageSize.height, imageSize.width, IMG_8UC3), r(imageSize.height, imageSize.width, IMG_8UC3);
-    l.upload(left + frame * next, (size_t)imageSize.width * 3, stream);
-    r.upload(right + frame * next, (size_t)imageSize.width * 3, stream);
-    cudaCheck(cudaStreamSynchronize((cudaStream_t)stream), "frame upload");
+    std::memcpy(staging, left + frame * next, frame);
+    std::memcpy(staging + frame, right + frame * next, frame);
+    l.upload(staging, (size_t)imageSize.width * 3, copyStream);
+    r.upload(staging + frame, (size_t)imageSize.width * 3, copyStream);
+    cudaCheck(cudaStreamSynchronize((cudaStream_t)copyStream), "frame upload");
     ++next;
     return std::make_shared<StereoDataElement>(l, r);
 }

@@ -5,22 +5,60 @@
 #include <cuda_runtime.h>
 
 #include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "../../../include/cartb200.h"
 
 namespace cart {
 
 namespace {
-struct StreamGuard {  // the reference creates and synchronises one stream per module call (e.g. derivative.cu:171-179)
+// The reference creates and synchronises one stream per module call (e.g. derivative.cu:171-179); here the streams are
+// recycled through a small pool instead of being created and destroyed for every frame and module.
+// (the event is kept for callers that prefer a blocking wait; StreamGuard::sync polls)
+struct PooledStream {
     cudaStream_t s = nullptr;
-    StreamGuard() {
-        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) throw std::runtime_error("cudaStreamCreate failed");
+    cudaEvent_t done = nullptr;
+};
+struct StreamPool {
+    std::mutex m;
+    std::vector<PooledStream> free;
+    PooledStream take() {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            if (!free.empty()) {
+                PooledStream s = free.back();
+                free.pop_back();
+                return s;
+            }
+        }
+        PooledStream s;
+        if (cudaStreamCreateWithFlags(&s.s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.done, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess)
+            throw std::runtime_error("cudaStreamCreate failed");
+        return s;
     }
-    ~StreamGuard() {
-        if (s) cudaStreamDestroy(s);
+    void give(PooledStream s) {
+        std::lock_guard<std::mutex> lock(m);
+        free.push_back(s);
     }
+};
+StreamPool& streamPool() {
+    static StreamPool* pool = new StreamPool();
+    return *pool;
+}
+struct StreamGuard {
+    PooledStream ps;
+    cudaStream_t s = nullptr;
+    StreamGuard() : ps(streamPool().take()), s(ps.s) {}
+    ~StreamGuard() { streamPool().give(ps); }  // every module synchronises the stream before it returns
+    // polling with yield: as fast as the default spin-wait when the host is idle, but a waiting module thread gives its
+    // core to whoever is runnable (the PNG decoders) - a blocking-sync event costs ~100 us of wake-up latency per module call
     void sync() {
-        if (cudaStreamSynchronize(s) != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError()));
+        cudaError_t e;
+        while ((e = cudaStreamQuery(s)) == cudaErrorNotReady) std::this_thread::yield();
+        if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
     }
 };
 }  // namespace

@@ -260,6 +260,7 @@ KITTIDataSource::~KITTIDataSource() {
         cudaFreeHost(s.left);
         cudaFreeHost(s.right);
     }
+    if (copyStream) cudaStreamDestroy((cudaStream_t)copyStream);
 }
 
 void KITTIDataSource::startPrefetch() {
@@ -332,9 +333,15 @@ std::shared_ptr<DataElement> KITTIDataSource::getNextInternal(void* stream) {
         if (slot->state == Slot::FAILED) throw std::runtime_error(slot->error);
     }
     image_t l(imageSize.height, imageSize.width, IMG_8UC3), r(imageSize.height, imageSize.width, IMG_8UC3);
-    l.upload(slot->left, (size_t)imageSize.width * 3, stream);  // pinned source: truly asynchronous copies
-    r.upload(slot->right, (size_t)imageSize.width * 3, stream);
-    syncStream(stream);  // the slot goes back to the decoders
+    if (!copyStream) {
+        cudaStream_t s = nullptr;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) throw std::runtime_error("cudaStreamCreate failed");
+        copyStream = s;
+    }
+    (void)stream;  // the caller's stream is the legacy default stream in System::startNewRun: use a private one
+    l.upload(slot->left, (size_t)imageSize.width * 3, copyStream);  // pinned source: truly asynchronous copies
+    r.upload(slot->right, (size_t)imageSize.width * 3, copyStream);
+    syncStream(copyStream);  // the slot goes back to the decoders
     {
         std::lock_guard<std::mutex> lock(ringMutex);
         slot->state = Slot::FREE;

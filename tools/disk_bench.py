@@ -54,6 +54,18 @@ def main():
     source = {"type": "kitti", "path": root, "sequence": 0}
     out = {"frames": args.frames, "png_bytes_per_image": png_bytes, "decode_ms_per_image_one_thread": decode_ms,
            "host_cores": os.cpu_count()}
+    # the same module list fed from host memory (no decode): what the module layer itself sustains
+    frames = [seq.frame(1 + (i % args.distinct))[:2] for i in range(args.distinct)]
+    Lm = np.stack([frames[i % args.distinct][0] for i in range(args.frames)])
+    Rm = np.stack([frames[i % args.distinct][1] for i in range(args.frames)])
+    host.run_config(modules, Lm[:8], Rm[:8], sequential=False)
+    for name, sq in (("memory_to_planes_fps_in_flight_12", False), ("memory_to_planes_fps_sequential", True)):
+        t0 = time.perf_counter()
+        host.run_config(modules, Lm, Rm, sequential=sq)
+        out[name] = args.frames / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    host.run_config(modules, Lm[:1], Rm[:1], sequential=True)
+    out["setup_plus_one_frame_s"] = time.perf_counter() - t0
     for threads in (1, 4, None):
         if threads:
             os.environ["CARTB200_KITTI_DECODE_THREADS"] = str(threads)
