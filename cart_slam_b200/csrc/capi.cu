@@ -313,6 +313,11 @@ int cartb200_create(const cartb200_config* cfg, cartb200_ctx** out) {
 
 void cartb200_destroy(cartb200_ctx* c) {
     if (!c) return;
+    for (int i = 0; i < 2; ++i) {
+        if (c->aggStream[i]) cudaStreamDestroy(c->aggStream[i]);
+        if (c->aggJoin[i]) cudaEventDestroy(c->aggJoin[i]);
+    }
+    if (c->aggFork) cudaEventDestroy(c->aggFork);
     cudaFree(c->grayL);
     cudaFree(c->grayR);
     cudaFree(c->censusL);

@@ -99,6 +99,10 @@ struct cartb200_ctx {
     double* spStats = nullptr;     // [B]{[labels][16] records, [labels][8] stored costs, [labels][16] deltas}
     int* spTileMap = nullptr;      // [tilesY][tilesX] index into spTileTab, -1 = interior tile
     uint32_t* spTileTab = nullptr; // [edge tiles][66*66] source pixel (y << 16 | x) of the reference's label tile
+    // the path kernels of one aggregation run on up to three streams (horizontal pair / vertical pair / diagonals) so
+    // that the last, partially filled wave of one launch is filled by the next (lazy)
+    cudaStream_t aggStream[2] = {nullptr, nullptr};
+    cudaEvent_t aggFork = nullptr, aggJoin[2] = {nullptr, nullptr};
     // sequence runner scratch (lazy)
     void* seq = nullptr;
 };

@@ -592,10 +592,12 @@ __global__ void __launch_bounds__(128) aggregate_diagonal_kernel(PathArgs a, int
 
 static const int kDirs[8][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}};
 
+// st[0]: horizontal paths, st[1]: vertical paths, st[2]: diagonals
 template <int D>
-static void launch_paths_D(cartb200_ctx* c, PathArgs a, int n, int p0, int p1, cudaStream_t s) {
+static void launch_paths_D(cartb200_ctx* c, PathArgs a, int n, int p0, int p1, cudaStream_t const (&st)[3]) {
     constexpr int GPB = 128 / (D / 16);
     for (int p = p0; p < p1; ++p) {
+        cudaStream_t s = kDirs[p][1] == 0 ? st[0] : (kDirs[p][0] == 0 ? st[1] : st[2]);
         a.vol = c->volumes + (size_t)p * c->volPathStride;
         a.dx = kDirs[p][0];
         a.dy = kDirs[p][1];
@@ -660,11 +662,49 @@ int launch_aggregate_range(cartb200_ctx* c, int n, int p0, int p1, cudaStream_t 
     static const int pfRows = getenv("CARTB200_PF_ROWS") ? atoi(getenv("CARTB200_PF_ROWS")) : 6;
     a.pfPixels = pfPixels;
     a.pfRows = pfRows;
+    // More than one path kind: fork onto the context's auxiliary streams.  Every launch ends in a partially filled wave
+    // (e.g. 3072 CTAs on 1184 slots = 2.6 waves for the horizontal pair of a 64-frame KITTI batch); CTAs of the next
+    // path kind fill it instead of waiting for the launch to drain.  CARTB200_AGG_STREAMS=0 keeps one stream.
+    static const bool multi = !(getenv("CARTB200_AGG_STREAMS") && atoi(getenv("CARTB200_AGG_STREAMS")) == 0);
+    bool kinds[3] = {false, false, false};
+    for (int p = p0; p < p1; ++p) kinds[kDirs[p][1] == 0 ? 0 : (kDirs[p][0] == 0 ? 1 : 2)] = true;
+    const bool fork = multi && (int)kinds[0] + (int)kinds[1] + (int)kinds[2] > 1;
+    cudaStream_t st[3] = {s, s, s};
+    if (fork) {
+        if (!c->aggFork) {
+            for (int i = 0; i < 2; ++i) {
+                CB_CHECK_CUDA(c, cudaStreamCreateWithFlags(&c->aggStream[i], cudaStreamNonBlocking));
+                CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&c->aggJoin[i], cudaEventDisableTiming));
+            }
+            CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&c->aggFork, cudaEventDisableTiming));
+        }
+        CB_CHECK_CUDA(c, cudaEventRecord(c->aggFork, s));
+        int next = 0;  // the first kind stays on the caller's stream
+        bool first = true;
+        for (int k = 0; k < 3; ++k) {
+            if (!kinds[k]) continue;
+            if (first) {
+                first = false;
+                continue;
+            }
+            st[k] = c->aggStream[next++];
+            CB_CHECK_CUDA(c, cudaStreamWaitEvent(st[k], c->aggFork, 0));
+        }
+    }
     switch (c->D) {
-        case 64: launch_paths_D<64>(c, a, n, p0, p1, s); break;
-        case 128: launch_paths_D<128>(c, a, n, p0, p1, s); break;
-        case 256: launch_paths_D<256>(c, a, n, p0, p1, s); break;
+        case 64: launch_paths_D<64>(c, a, n, p0, p1, st); break;
+        case 128: launch_paths_D<128>(c, a, n, p0, p1, st); break;
+        case 256: launch_paths_D<256>(c, a, n, p0, p1, st); break;
         default: c->err = "num_disparities must be 64, 128 or 256"; return CARTB200_E_UNSUPPORTED;
+    }
+    if (fork) {
+        int next = 0;
+        for (int k = 0; k < 3; ++k) {
+            if (st[k] == s) continue;
+            CB_CHECK_CUDA(c, cudaEventRecord(c->aggJoin[next], st[k]));
+            CB_CHECK_CUDA(c, cudaStreamWaitEvent(s, c->aggJoin[next], 0));
+            ++next;
+        }
     }
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) {
