@@ -545,7 +545,13 @@ __device__ __forceinline__ void diagonal_body(const PathArgs& a, int dy, uint8_t
 #pragma unroll
         for (int i = 0; i < 8; ++i) dp[c][i] = 0;
     }
-    for (int s4 = 0; s4 < H; s4 += 4) {
+    // Steps at which at least one of the warp's columns is inside the image: x = u0 + c + DX * step in [0, W).  Before a
+    // path enters the image its state is zero (costs are masked) and after it has left nothing is stored, so the steps
+    // outside this range are skipped: the sweep costs W * H pixel steps instead of (W + H) * H (the corner triangles).
+    int lo = DX > 0 ? -u0 - 3 : u0 - (W - 1), hi = DX > 0 ? W - 1 - u0 : u0 + 3;
+    lo = __reduce_min_sync(0xFFFFFFFFu, max(lo, 0));
+    hi = __reduce_max_sync(0xFFFFFFFFu, min(hi, H - 1));
+    for (int s4 = lo & ~3; s4 <= hi; s4 += 4) {
         const int base4 = u0 + DX * s4;  // multiple of 4
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
