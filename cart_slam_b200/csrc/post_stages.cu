@@ -23,18 +23,38 @@ struct DispAccessor {
 __global__ void __launch_bounds__(256) interpolate_kernel(ImgBatch<const int16_t> src, ImgBatch<int16_t> dst, int W,
                                                           int H, int radius, int iterations, int minD, int maxD) {
     extern __shared__ int16_t sm[];
+    __shared__ unsigned recipM[128];  // ceil(2^32 / count) for the window counts 1 .. (2 radius - 1)^2
     const int pad = radius - 1, S = 64 + 2 * pad, N = S * S;
+    if (threadIdx.x >= 1 && threadIdx.x < 128) recipM[threadIdx.x] = 0xFFFFFFFFu / threadIdx.x + 1u;
     int16_t* cur = sm;
     int16_t* nxt = sm + N;
     const int bx = blockIdx.x, by = blockIdx.y, f = blockIdx.z;
     TileGeom g{W, H, 64, 64, pad, pad, 4, 4, N};
     DispAccessor acc{src.frame(f)};
     TileEval<int16_t, DispAccessor> te(acc, g, bx, by, kInvalid);
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const int ly = i / S - pad, lx = i % S - pad;
-        const int16_t v = te.template value<true>(lx, ly);
-        cur[i] = v;
-        nxt[i] = v;
+    // A tile whose padded extent lies inside the image gets no halo phase from the reference's loader: its shared tile is
+    // the body copy alone, i.e. the image read pad rows further down (TileEval::body with pXS = startX - pad,
+    // pYS = startY - pad reduces to image(startX + lx, startY + ly + pad)).  The general closed form (divisions by the
+    // run-time tile stride, the four halo rules) is only evaluated for the tiles on the image border.
+    const bool interior = bx * 64 - pad >= 0 && by * 64 - pad >= 0 && bx * 64 + 64 + pad <= W && by * 64 + 64 + pad <= H;
+    if (interior) {
+        const Img<const int16_t> im = src.frame(f);
+        for (int r = threadIdx.x / 32; r < S; r += blockDim.x / 32) {  // one warp per tile row: coalesced, no division
+            const int y = by * 64 + r;  // = startY + (r - pad) + pad
+            for (int cidx = threadIdx.x % 32; cidx < S; cidx += 32) {
+                const int x = bx * 64 + cidx - pad;
+                const int16_t v = y < H ? __ldg(im.row(y) + x) : kInvalid;
+                cur[r * S + cidx] = v;
+                nxt[r * S + cidx] = v;
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const int ly = i / S - pad, lx = i % S - pad;
+            const int16_t v = te.template value<true>(lx, ly);
+            cur[i] = v;
+            nxt[i] = v;
+        }
     }
     __syncthreads();
     const unsigned minCount = (unsigned)(radius * radius + 1);
@@ -54,7 +74,10 @@ __global__ void __launch_bounds__(256) interpolate_kernel(ImgBatch<const int16_t
                     }
                 }
             }
-            nxt[(ly + pad) * S + lx + pad] = count > minCount ? (int16_t)(sum / (int)count) : kInvalid;
+            // sum / count for 0 <= sum < 2^28 and count <= 81 by a rounded-up reciprocal (exact: sum * (M count - 2^32) < 2^32)
+            int16_t res = kInvalid;
+            if (count > minCount) res = (int16_t)__umulhi((unsigned)sum, recipM[count]);
+            nxt[(ly + pad) * S + lx + pad] = res;
         }
         __syncthreads();
         int16_t* t = cur;
@@ -79,7 +102,7 @@ int launch_interpolate_from(cartb200_ctx* c, int n, ImgBatch<const int16_t> src,
                             int iterations, int minD, int maxD, cudaStream_t s) {
     const int pad = radius - 1, S = 64 + 2 * pad;
     const size_t smem = (size_t)2 * S * S * sizeof(int16_t);
-    if (smem > 200 * 1024) {
+    if (smem > 200 * 1024 || (2 * radius - 1) * (2 * radius - 1) > 127) {
         c->err = "interpolate: smoothing radius too large for shared memory";
         return CARTB200_E_UNSUPPORTED;
     }
