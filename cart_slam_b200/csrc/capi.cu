@@ -855,6 +855,18 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
     }
     const bool peak = o->provider == 1;
     const bool sp = o->pipeline == 1;
+    // Whatever path leaves this function early (an error code from a launch or a copy), work that was already queued on
+    // the internal streams must not outlive the call: the caller may free or reuse its buffers as soon as it sees the
+    // error.  On success the streams have been joined back into `s` (or synchronised) by the code below.
+    struct JoinOnError {
+        SeqScratch* q;
+        bool ok = false;
+        ~JoinOnError() {
+            if (ok) return;
+            if (q->spStream) cudaStreamSynchronize(q->spStream);
+            if (q->copyStream) cudaStreamSynchronize(q->copyStream);
+        }
+    } joinGuard{q};
     // storage
     if (inputsOnHost) {
         if ((rc = ensureCap(c, &q->inL, &q->inCap, bgrFrame * n))) return rc;
@@ -950,10 +962,10 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
             CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
             q->phase1Frames = n;
             q->phase1Pipeline = 0;
-            return CARTB200_OK;
+            return joinGuard.ok = true, CARTB200_OK;
         }
         if (outputsOnHost || inputsOnHost) CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
-        return CARTB200_OK;
+        return joinGuard.ok = true, CARTB200_OK;
     }
 
     // ---------------- superpixel pipeline ------------------------------------------------------------
@@ -989,7 +1001,7 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
     if (phase == 2) {
         if ((rc = votePhase(paramsIn))) return rc;
         if (outputsOnHost) CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
-        return CARTB200_OK;
+        return joinGuard.ok = true, CARTB200_OK;
     }
     const bool deferVote = peak || phase == 1;  // parameters are only known once every frame's histogram is
     if (!deferVote) {  // static ranges are the same for every frame: upload them once
@@ -1151,7 +1163,7 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
             }
             q->phase1Frames = n;
             q->phase1Pipeline = 1;
-            return CARTB200_OK;
+            return joinGuard.ok = true, CARTB200_OK;
         }
         if ((rc = votePhase(q->paramsHost))) return rc;
     }
@@ -1160,7 +1172,7 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
         if (dispOut) CB_CHECK_CUDA(c, cudaMemcpyAsync(dispOut, dispDev, pxFrame * 2 * n, cudaMemcpyDeviceToHost, s));
     }
     if (outputsOnHost || inputsOnHost) CB_CHECK_CUDA(c, cudaStreamSynchronize(s));
-    return CARTB200_OK;
+    return joinGuard.ok = true, CARTB200_OK;
 }
 
 }  // namespace

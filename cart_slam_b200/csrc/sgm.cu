@@ -728,9 +728,10 @@ int launch_aggregate_range(cartb200_ctx* c, int n, int p0, int p1, cudaStream_t 
 //     uniqueness test and integer sub-pixel refinement on the group's first lane (the two neighbours of the
 //     winner come from a per-group shared-memory stash of the summed vector);
 //   * right image: dR(r) = argmin_d S(r + d, d) is accumulated systolically - a running minimum per
-//     disparity slot that moves one slot up per pixel (register renaming by a 16-fold unroll, one shuffle per
-//     step between lanes), so a right pixel leaves the last slot exactly when all its candidates have been
-//     seen.  Results are merged into a u32 key image with atomicMin, which also joins the partial minima of
+//     disparity slot that moves one slot up per pixel (RM[j] = min(RM[j-1], key[j]) in descending order: the shift is
+//     free, one shuffle per step between lanes), so a right pixel leaves the last slot exactly when all its candidates
+//     have been seen.  The step loop is only unrolled by the cp.async ring depth: a 16-fold unrolled body (56 KB of
+//     code) made instruction fetch the kernel's first stall reason.  Results are merged into a u32 key image with atomicMin, which also joins the partial minima of
 //     adjacent segments.  No shared-memory ring, no modulo arithmetic, no block barrier.
 struct WtaArgs {
     const uint8_t* vol;
@@ -768,7 +769,7 @@ __device__ __forceinline__ void top2_of16(const uint32_t (&k)[16], uint32_t& b1,
     b2 = hi[0];
 }
 
-constexpr int kWtaDepth = 4;  // must divide 16 (the stage index is t % kWtaDepth inside the 16-step unrolled body)  // pixels in flight per lane (cp.async ring)
+constexpr int kWtaDepth = 4;  // pixels in flight per lane (cp.async ring) = unroll factor of the step loop; divides 16
 template <int D, int P>
 __global__ void __launch_bounds__(128, 5) wta_walk_kernel(WtaArgs a) {
     constexpr int LPP = D / 16;
@@ -801,7 +802,7 @@ __global__ void __launch_bounds__(128, 5) wta_walk_kernel(WtaArgs a) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) J[k] = (dbase + 4 * k) * 0x01010101u + 0x03020100u;
 
-    uint32_t RM[16];  // running minima; logical slot j (disparity dbase + j) at step t lives in RM[(j - t) & 15]
+    uint32_t RM[16];  // running minima; slot j = disparity dbase + j
 #pragma unroll
     for (int j = 0; j < 16; ++j) RM[j] = kKeyInf;
     // The volume vectors are staged through a per-thread shared-memory ring with cp.async (LDGSTS): kWtaDepth
@@ -816,10 +817,10 @@ __global__ void __launch_bounds__(128, 5) wta_walk_kernel(WtaArgs a) {
         __pipeline_commit();
     }
 
-    for (int t0 = 0; t0 < T; t0 += 16, vp += 16 * D) {
-        const bool blockActive = __all_sync(0xFFFFFFFFu, x0 + t0 + 16 <= x1);
+    for (int t0 = 0; t0 < T; t0 += kWtaDepth, vp += kWtaDepth * D) {
+        const bool blockActive = __all_sync(0xFFFFFFFFu, x0 + t0 + kWtaDepth <= x1);
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
+        for (int t = 0; t < kWtaDepth; ++t) {
             const int x = x0 + t0 + t;
             const bool act = x < x1;
             __pipeline_wait_prior(kWtaDepth - 1);  // the oldest stage (this pixel) has landed
@@ -887,24 +888,23 @@ __global__ void __launch_bounds__(128, 5) wta_walk_kernel(WtaArgs a) {
                 if (act && lane == 0) outL[x] = reject ? (uint16_t)0xFFFF : (uint16_t)((d1 << 4) + q);
             }
             // ---- right: systolic running minima ----
-            const int ph = (16 - t) & 15;  // physical register of logical slot 0 at this step (static after unrolling)
-            const uint32_t out = RM[ph];   // slot 15 of the previous step: its right pixel moves on to the next lane
+            const uint32_t out = RM[15];  // slot 15 of the previous step: its right pixel moves on to the next lane
             uint32_t in = __shfl_up_sync(0xFFFFFFFFu, out, 1, LPP);
             if (lane == 0) in = kKeyInf;
             if (lane == LPP - 1 && out < kKeyReal) {
                 const int r = x - 1 - (D - 1);  // complete: every candidate x' in [r, r + D) has been seen
                 if (r >= 0) atomicMin(rk + r, out);
             }
-            RM[ph] = min(in, key[0]);
 #pragma unroll
-            for (int j = 1; j < 16; ++j) RM[(j + 16 - t) & 15] = min(RM[(j + 16 - t) & 15], key[j]);
+            for (int j = 15; j >= 1; --j) RM[j] = min(RM[j - 1], key[j]);  // every minimum moves one slot up
+            RM[0] = min(in, key[0]);
         }
     }
-    // flush: the last step had t = 15, so slot j sits in RM[(j + 1) & 15] and belongs to right pixel (x0 + T - 1) - d
+    // flush: slot j belongs to right pixel (x0 + T - 1) - d
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const int r = x0 + T - 1 - (int)(dbase + j);
-        const uint32_t val = RM[(j + 1) & 15];
+        const uint32_t val = RM[j];
         if (r >= 0 && r < W && val < kKeyReal) atomicMin(rk + r, val);
     }
 }
