@@ -244,10 +244,34 @@ def module_layer_arm(L, R, n_frames: int = 96):
             res[name] = n / (time.perf_counter() - t0)
         return {"value": res["in_flight_12"], "unit": UNIT, "sequential_value": res["sequential"], "frames": n,
                 "what": "cartb200_host_run_config: per-frame SystemModule::run calls (n = 1 per C-ABI call, one context per module, "
-                        "a stream created and synchronised per call as the reference does), kitti-planeseg.json module list minus "
+                        "one stream synchronised per call as the reference does), kitti-planeseg.json module list minus "
                         "out-of-scope modules, host frames in / host planes out, wall clock; value = up to 12 frames in flight"}
     except Exception as e:  # reported, never fatal
         return {"error": str(e)}
+
+
+def other_configs():
+    """BASELINE.json configs[2] / configs[3] and the naive pipeline, each measured by a child `bench.py --extra 0` on a short
+    sequence (the full-length lines are under profiles/): keeps every configuration of BASELINE.json in the driver's record."""
+    runs = {
+        "zed_config2": ["--workload", "zed", "--frames", "64"],
+        "4k_8path_config3": ["--workload", "4k", "--frames", "8"],
+        "kitti_naive_pipeline": ["--workload", "kitti", "--pipeline", "0", "--frames", "256"],
+    }
+    out = {}
+    for name, extra_args in runs.items():
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--steps", "2", "--warmup", "3", "--extra", "0"] + extra_args,
+                               capture_output=True, text=True, timeout=420, cwd=ROOT)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+            d = json.loads(line)
+            out[name] = {"metric": d["metric"], "value": d["value"], "unit": d["unit"], "e2e": d["e2e"]["value"],
+                         "ms_per_step": d["ms_per_step"], "steps": d["steps"], "warmup": d["warmup"],
+                         "aggregation_roofline_frac": (d.get("roofline") or {}).get("frac"), "config": d["config"]["workload"],
+                         "frames": d["config"]["frames_per_gpu"], "batch": d["config"]["batch"]}
+        except Exception as e:  # reported, never fatal
+            out[name] = {"error": str(e)[:300]}
+    return out
 
 
 def cpu_arm(n_sample: int, L, R):
@@ -307,6 +331,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="frames per batched launch (SGM stages); superpixel slots = sequence chunks")
     ap.add_argument("--pipeline", type=int, default=None, help="1 = superpixel pipeline (headline), 0 = naive")
     ap.add_argument("--cpu-sample", type=int, default=6)
+    ap.add_argument("--extra", type=int, default=1,
+                    help="N = 1 kitti run only: also measure BASELINE.json configs[2] (zed), configs[3] (4k, 8 paths) and the naive "
+                         "pipeline on short sequences (each in a child process) and report them under `other_configs`")
     ap.add_argument("--sp-exact", type=int, default=1, help="accepted for old command lines; ignored (the approximate mode is gone)")
     args = ap.parse_args()
     global W, H, D, METRIC
@@ -372,7 +399,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hbm_peak, peak_src = load_peaks()
 
-    from cart_slam_b200.parallel import plan_shards
+    from cart_slam_b200.parallel import allgather_histograms, plan_shards
 
     sharded = world > 1
     RESET = 64
@@ -414,16 +441,11 @@ def main():
     gather_buf = None
     if sharded and rank == 0:
         gather_buf = [torch.empty_like(planes_dev) for _ in range(world)]
-    hist_pad = torch.zeros((max_count, 256), dtype=torch.int32, device="cuda") if sharded else None
-    hist_all = torch.empty((world * max_count, 256), dtype=torch.int32, device="cuda") if sharded else None
 
     def exchange_parameters(hist):
         """the only data-path collective besides the result gather: all-gather of the per-frame histograms, then the
         reference's parameter schedule over the whole sequence on the CPU (every rank computes the same table)"""
-        hist_pad[:n].copy_(torch.from_numpy(hist), non_blocking=False)
-        dist.all_gather_into_tensor(hist_all, hist_pad)
-        ha = hist_all.cpu().numpy().reshape(world, max_count, 256)
-        full = np.concatenate([ha[r, :shards[r].count] for r in range(world)])
+        full = allgather_histograms(hist, shards, device="cuda")
         return cb.sequence_parameters(seq_opts(1), full)[my.frame_slice]
 
     def compute_device():
@@ -523,11 +545,18 @@ def main():
     cpu = None
     ref_gpu = None
     module_layer = None
+    scratch_bytes = ctx.scratch_bytes()
     if rank == 0 and world == 1 and args.workload == "kitti":  # the other workloads are recorded without CPU arms
         v, threads, sample = cpu_arm(args.cpu_sample, L, R)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
         ref_gpu = reference_gpu_kernels()
         module_layer = module_layer_arm(L, R)
+    others = None
+    if rank == 0 and world == 1 and args.workload == "kitti" and args.pipeline == 1 and args.extra:
+        ctx.close()  # give the memory back before the child processes allocate theirs
+        del devL, devR, planes_dev
+        torch.cuda.empty_cache()
+        others = other_configs()
 
     if rank == 0:
         total_frames = total * args.steps
@@ -551,8 +580,8 @@ def main():
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(2 * total * H * W * 3), "d2h_bytes_per_step": int(total * H * W)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "reference_gpu_kernels": ref_gpu, "module_layer": module_layer,
-            "library": cb.version(), "scratch_bytes": ctx.scratch_bytes(),
+            "reference_gpu_kernels": ref_gpu, "module_layer": module_layer, "other_configs": others,
+            "library": cb.version(), "scratch_bytes": scratch_bytes,
         }
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + "\n").encode())

@@ -106,6 +106,7 @@ def _load():
     lib.cartb200_region_inliers.argtypes = [vp, vp, sz, vp, sz, i, vp, i, C.c_double, vp, vp]
     lib.cartb200_run_sequence_host.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp, vp]
     lib.cartb200_run_sequence_device.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp, vp, vp]
+    lib.cartb200_resize_bgr8.argtypes = [vp, sz, i, i, vp, sz, i, i, vp]
     lib.cartb200_run_sequence_phase1_device.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp, vp, vp]
     lib.cartb200_run_sequence_phase2_device.argtypes = [vp, C.POINTER(_CSeqOpts), i, vp, vp, vp]
     lib.cartb200_sequence_parameters.argtypes = [C.POINTER(_CSeqOpts), i, vp, vp]
@@ -141,8 +142,20 @@ EXPORTED_SYMBOLS = [
     "cartb200_sp_planeseg", "cartb200_histogram_peak_update", "cartb200_default_sequence_opts",
     "cartb200_run_sequence_host", "cartb200_run_sequence_device", "cartb200_run_sequence_phase1_device",
     "cartb200_run_sequence_phase2_device", "cartb200_run_sequence_phase1_host", "cartb200_run_sequence_phase2_host",
-    "cartb200_sequence_parameters", "cartb200_debug_ref_tile_i32",
+    "cartb200_sequence_parameters", "cartb200_resize_bgr8", "cartb200_debug_ref_tile_i32",
 ]
+
+
+def resize_bgr8(src, dw: int, dh: int):
+    """cv::cuda::resize(..., INTER_LINEAR) replacement for CV_8UC3 device images: src = uint8 CUDA tensor [H, W, 3]."""
+    import torch
+    assert src.is_cuda and src.dtype == torch.uint8 and src.dim() == 3 and src.shape[2] == 3 and src.is_contiguous()
+    out = torch.empty((dh, dw, 3), dtype=torch.uint8, device=src.device)
+    rc = _lib.cartb200_resize_bgr8(src.data_ptr(), src.shape[1] * 3, src.shape[1], src.shape[0], out.data_ptr(), dw * 3, dw, dh,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        raise CartB200Error(rc, "resize_bgr8 failed")
+    return out
 
 
 def sequence_parameters(opts: "SequenceOptions", hist: np.ndarray) -> np.ndarray:

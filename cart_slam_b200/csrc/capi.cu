@@ -659,6 +659,11 @@ int cartb200_depth(cartb200_ctx* c, int n, const int16_t* d, size_t dp, size_t d
     return launch_depth(c, n, ImgBatch<const int16_t>{d, dp, dfs}, ImgBatch<float>{xyz, xp, xfs}, q16Host, (cudaStream_t)stream);
 }
 
+int cartb200_resize_bgr8(const uint8_t* src, size_t sp, int sw, int sh, uint8_t* dst, size_t dp, int dw, int dh, void* stream) {
+    if (!src || !dst || sw < 1 || sh < 1 || dw < 1 || dh < 1 || sp < (size_t)sw * 3 || dp < (size_t)dw * 3) return CARTB200_E_ARG;
+    return launch_resize_bgr8(src, sp, sw, sh, dst, dp, dw, dh, (cudaStream_t)stream);
+}
+
 int cartb200_histogram_peak_update(const int32_t* hist, int32_t* params) {
     if (!hist || !params) return CARTB200_E_ARG;
     return cb::histogram_peak_update(hist, params);

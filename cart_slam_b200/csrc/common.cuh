@@ -150,6 +150,7 @@ int launch_overlay_planes(cartb200_ctx* c, Img<const uint8_t> bgr, Img<const uin
 int launch_overlay_boundaries(cartb200_ctx* c, Img<const uint8_t> bgr, Img<const uint16_t> labels, Img<uint8_t> out, cudaStream_t s);
 int launch_depth(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<float> xyz, const float* q16Host, cudaStream_t s);
 int launch_border_map(cartb200_ctx* c, Img<const uint16_t> labels, Img<uint8_t> border, cudaStream_t s);
+int launch_resize_bgr8(const uint8_t* src, size_t srcPitch, int sw, int sh, uint8_t* dst, size_t dstPitch, int dw, int dh, cudaStream_t s);
 // per-device kernel attributes (dynamic shared memory limits), applied by cartb200_create on the context's device
 cudaError_t sgm_set_kernel_attributes();
 cudaError_t post_set_kernel_attributes();

@@ -127,30 +127,73 @@ int launch_interpolate(cartb200_ctx* c, int n, ImgBatch<int16_t> disp, int radiu
 }
 
 // ---------------------------------------------------------------------------------------------
+// cv::cuda::resize(src, dst, size, 0, 0, INTER_LINEAR) on CV_8UC3 - the KITTI source's optional resize
+// (/root/reference/src/sources/kitti.cpp:166-169).  Normative behaviour: oracle/stages.cpp orc_resize_bgr8 (the same
+// float operations in the same order, no FMA contraction: bit-identical to it; parity against OpenCV itself is unpinned).
+__global__ void __launch_bounds__(256) resize_bgr8_kernel(const uint8_t* __restrict__ src, size_t srcPitch, int sw, int sh,
+                                                          uint8_t* __restrict__ dst, size_t dstPitch, int dw, int dh, float fx,
+                                                          float fy) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw) return;
+    const float sx = (float)x * fx, sy = (float)y * fy;
+    const int x1 = __float2int_rd(sx), y1 = __float2int_rd(sy);
+    const int x2 = x1 + 1, y2 = y1 + 1;
+    const int x1r = min(x1, sw - 1), y1r = min(y1, sh - 1), x2r = min(x2, sw - 1), y2r = min(y2, sh - 1);
+    const float w11 = ((float)x2 - sx) * ((float)y2 - sy), w12 = (sx - (float)x1) * ((float)y2 - sy);
+    const float w21 = ((float)x2 - sx) * (sy - (float)y1), w22 = (sx - (float)x1) * (sy - (float)y1);
+    const uint8_t *r1 = src + (size_t)y1r * srcPitch, *r2 = src + (size_t)y2r * srcPitch;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float out = 0.0f;
+        out = out + (float)__ldg(r1 + 3 * x1r + c) * w11;
+        out = out + (float)__ldg(r1 + 3 * x2r + c) * w12;
+        out = out + (float)__ldg(r2 + 3 * x1r + c) * w21;
+        out = out + (float)__ldg(r2 + 3 * x2r + c) * w22;
+        dst[(size_t)y * dstPitch + 3 * x + c] = (uint8_t)min(255, max(0, __float2int_rn(out)));
+    }
+}
+
+int launch_resize_bgr8(const uint8_t* src, size_t srcPitch, int sw, int sh, uint8_t* dst, size_t dstPitch, int dw, int dh,
+                       cudaStream_t s) {
+    const float fx = (float)(1.0 / ((double)dw / (double)sw)), fy = (float)(1.0 / ((double)dh / (double)sh));
+    dim3 grid(ceilDiv(dw, 256), dh);
+    resize_bgr8_kernel<<<grid, 256, 0, s>>>(src, srcPitch, sw, sh, dst, dstPitch, dw, dh, fx, fy);
+    return cudaPeekAtLastError() == cudaSuccess ? CARTB200_OK : CARTB200_E_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
 // calculateDirectionalDerivatives + mergeDerivativeHistograms,
 // /root/reference/src/modules/disparity/derivative.cu:27-116.
-// CTA = 128 x 8 pixels of one reference tile row band; thread = one column, 8 rows.
-constexpr int kDerivRows = 8;
+// CTA = one 128-column reference tile x a band of kDerivRows local rows.  The band's rows -2 .. +2 of the reference's
+// (bug-compatible) tile are staged in shared memory once - one closed-form evaluation per staged element, 1.3 per pixel,
+// where reading the four taps of every pixel straight through the closed form cost 4 - then thread = one column.
+constexpr int kDerivRows = 16;
 __global__ void __launch_bounds__(128) derivative_kernel(ImgBatch<const int16_t> disp, ImgBatch<int16_t> deriv,
                                                          int32_t* __restrict__ hist, int W, int H) {
     __shared__ int sh[512];
+    __shared__ int16_t tile[kDerivRows + 4][132];  // local rows r0 - 2 .. r0 + kDerivRows + 1, columns -2 .. 129
     for (int i = threadIdx.x; i < 512; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    const int f = blockIdx.z;
-    const int x = blockIdx.x * 128 + threadIdx.x;
-    const int y0 = blockIdx.y * kDerivRows;
-    if (x < W) {
+    const int f = blockIdx.z, bx = blockIdx.x;
+    constexpr int bandsPerTile = 128 / kDerivRows;
+    const int by = blockIdx.y / bandsPerTile, r0 = (blockIdx.y % bandsPerTile) * kDerivRows;
+    if (by * 128 + r0 < H) {  // uniform per CTA
         TileGeom g{W, H, 128, 128, 2, 2, 4, 4, 132 * 132};
         DispAccessor acc{disp.frame(f)};
-        const int bx = x >> 7, lx = x & 127;
+        TileEval<int16_t, DispAccessor> te(acc, g, bx, by, kInvalid);
+        for (int i = threadIdx.x; i < (kDerivRows + 4) * 132; i += blockDim.x) {
+            const int k = i / 132, cidx = i - k * 132;
+            tile[k][cidx] = te.template value<true>(cidx - 2, r0 - 2 + k);
+        }
+    }
+    __syncthreads();
+    const int lx = threadIdx.x, x = bx * 128 + lx;
+    if (x < W) {
         Img<int16_t> out = deriv.frame(f);
         for (int r = 0; r < kDerivRows; ++r) {
-            const int y = y0 + r;
+            const int y = by * 128 + r0 + r;
             if (y >= H) break;
-            const int by = y >> 7, ly = y & 127;
-            TileEval<int16_t, DispAccessor> te(acc, g, bx, by, kInvalid);
-            const int16_t up = te.template value<true>(lx, ly - 2), dn = te.template value<true>(lx, ly + 2);
-            const int16_t lf = te.template value<true>(lx - 2, ly), rt = te.template value<true>(lx + 2, ly);
+            const int16_t up = tile[r][lx + 2], dn = tile[r + 4][lx + 2];
+            const int16_t lf = tile[r + 2][lx], rt = tile[r + 2][lx + 4];
             const int16_t dv = (int16_t)(dn - up), dh = (int16_t)(rt - lf);
             const bool vv = up != kInvalid && dn != kInvalid, hv = lf != kInvalid && rt != kInvalid;
             short2 o;
@@ -169,7 +212,7 @@ __global__ void __launch_bounds__(128) derivative_kernel(ImgBatch<const int16_t>
 int launch_derivative(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp, ImgBatch<int16_t> deriv, int32_t* hist,
                       cudaStream_t s) {
     CB_CHECK_CUDA(c, cudaMemsetAsync(hist, 0, (size_t)n * 512 * sizeof(int32_t), s));
-    dim3 grid(ceilDiv(c->W, 128), ceilDiv(c->H, kDerivRows), n);
+    dim3 grid(ceilDiv(c->W, 128), ceilDiv(c->H, 128) * (128 / kDerivRows), n);
     derivative_kernel<<<grid, 128, 0, s>>>(disp, deriv, hist, c->W, c->H);
     CB_LAUNCH_CHECK(c);
     return CARTB200_OK;

@@ -45,6 +45,7 @@ class KITTIDataSource : public DataSource {
     void startPrefetch();
     void prefetchWorker();
     std::string path;
+    Size fileSize;  // size of the PNG files; imageSize (DataSource) is what the modules get
     int currentFrame = 0;
     std::vector<uint8_t> bufL, bufR;
     // prefetch ring: frame f lives in slot f % ring.size()

@@ -109,7 +109,11 @@ std::shared_ptr<DataSource> createDataSourceFromText(const std::string& text) {
     if (!cfg.is_object()) throw std::runtime_error("Data source configuration is not an object.");
     const std::string sourcePath = cfg.at("path").get<std::string>();
     const std::string type = cfg.at("type").get<std::string>();
-    if (type == "kitti") return std::make_shared<sources::KITTIDataSource>(sourcePath, get(cfg, "sequence", 0));
+    // "width" / "height" (extension): the imageSize constructor argument of KITTIDataSource (kitti.hpp:12), which the
+    // reference's JSON does not expose; frames are resized on the device when it differs from the files' size
+    if (type == "kitti")
+        return std::make_shared<sources::KITTIDataSource>(sourcePath, get(cfg, "sequence", 0),
+                                                          Size(get(cfg, "width", 0), get(cfg, "height", 0)));
     if (type == "zed") throw std::runtime_error("Data source type zed needs the proprietary ZED SDK (outside the scope of this build).");
     throw std::runtime_error("Unknown data source type.");
 }

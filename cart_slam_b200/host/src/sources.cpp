@@ -2,6 +2,8 @@
 #include "cart/sources.hpp"
 
 #include <cuda_runtime.h>
+
+#include "../../../include/cartb200.h"
 #include <sys/stat.h>
 #include <zlib.h>
 
@@ -228,8 +230,7 @@ void KITTIDataSource::init() {
     int w = 0, h = 0;
     util::readPngBgr(framePath(kLeftCam, 0), bufL, w, h);
     if (imageSize.width == 0 || imageSize.height == 0) imageSize = Size(w, h);
-    if (imageSize.width != w || imageSize.height != h)
-        throw std::runtime_error("KITTIDataSource: resizing (cv::cuda::resize, kitti.cpp:166-169) is not supported; use the native image size");
+    fileSize = Size(w, h);  // frames of another size than imageSize are resized on the device (kitti.cpp:166-169)
     const float scaleWidth = (float)imageSize.width / (float)w, scaleHeight = (float)imageSize.height / (float)h;
     // reprojection matrix, kitti.cpp:141-148
     CameraIntrinsics k;
@@ -270,7 +271,7 @@ void KITTIDataSource::startPrefetch() {
     size_t depth = 2 * (size_t)threads;
     if (const char* e = getenv("CARTB200_KITTI_RING"))
         if (atoi(e) > 0) depth = (size_t)atoi(e);
-    const size_t bytes = (size_t)imageSize.width * imageSize.height * 3;
+    const size_t bytes = (size_t)fileSize.width * fileSize.height * 3;
     ring.resize(depth);
     for (auto& s : ring)
         if (cudaMallocHost((void**)&s.left, bytes) != cudaSuccess || cudaMallocHost((void**)&s.right, bytes) != cudaSuccess)
@@ -281,7 +282,7 @@ void KITTIDataSource::startPrefetch() {
 // Each worker claims the next frame whose slot is free, decodes both images into the slot and marks it ready.
 void KITTIDataSource::prefetchWorker() {
     std::vector<uint8_t> tmp;
-    const size_t bytes = (size_t)imageSize.width * imageSize.height * 3;
+    const size_t bytes = (size_t)fileSize.width * fileSize.height * 3;
     for (;;) {
         int frame;
         Slot* slot;
@@ -304,7 +305,7 @@ void KITTIDataSource::prefetchWorker() {
                 int w = 0, h = 0;
                 for (int cam = 0; cam < 2; ++cam) {
                     util::readPngBgr(framePath(cam ? kRightCam : kLeftCam, frame), tmp, w, h);
-                    if (w != imageSize.width || h != imageSize.height)
+                    if (w != fileSize.width || h != fileSize.height)
                         throw std::runtime_error("KITTIDataSource: frame " + std::to_string(frame) + " has a different size");
                     std::memcpy(cam ? slot->right : slot->left, tmp.data(), bytes);
                 }
@@ -339,8 +340,20 @@ std::shared_ptr<DataElement> KITTIDataSource::getNextInternal(void* stream) {
         copyStream = s;
     }
     (void)stream;  // the caller's stream is the legacy default stream in System::startNewRun: use a private one
-    l.upload(slot->left, (size_t)imageSize.width * 3, copyStream);  // pinned source: truly asynchronous copies
-    r.upload(slot->right, (size_t)imageSize.width * 3, copyStream);
+    if (fileSize.width == imageSize.width && fileSize.height == imageSize.height) {
+        l.upload(slot->left, (size_t)imageSize.width * 3, copyStream);  // pinned source: truly asynchronous copies
+        r.upload(slot->right, (size_t)imageSize.width * 3, copyStream);
+    } else {  // cv::cuda::resize(..., INTER_LINEAR) of both images, kitti.cpp:166-169
+        image_t nl(fileSize.height, fileSize.width, IMG_8UC3), nr(fileSize.height, fileSize.width, IMG_8UC3);
+        nl.upload(slot->left, (size_t)fileSize.width * 3, copyStream);
+        nr.upload(slot->right, (size_t)fileSize.width * 3, copyStream);
+        if (cartb200_resize_bgr8(nl.as<uint8_t>(), nl.pitch, fileSize.width, fileSize.height, l.as<uint8_t>(), l.pitch,
+                                 imageSize.width, imageSize.height, copyStream) != 0 ||
+            cartb200_resize_bgr8(nr.as<uint8_t>(), nr.pitch, fileSize.width, fileSize.height, r.as<uint8_t>(), r.pitch,
+                                 imageSize.width, imageSize.height, copyStream) != 0)
+            throw std::runtime_error("KITTIDataSource: resize failed");
+        syncStream(copyStream);  // nl / nr go back to the image pool when they leave this scope
+    }
     syncStream(copyStream);  // the slot goes back to the decoders
     {
         std::lock_guard<std::mutex> lock(ringMutex);

@@ -85,3 +85,26 @@ def gather_to_rank0(local, shards: Sequence[Shard], group=None):
     if rank != 0:
         return None
     return torch.cat([out[s.rank][: s.count] for s in shards], dim=0)
+
+
+def allgather_histograms(local_hist, shards: Sequence[Shard], group=None, device=None):
+    """Second collective of the sharded runner (the two-pass histogram_peak scheme): every rank
+    contributes the per-frame histograms of its shard ([count, 256] int32, numpy, as phase 1 returns them) and every
+    rank gets the whole sequence's [n, 256] table in frame order.  Shards are padded to the longest one (all_gather
+    wants equal sizes).  `device`: where the exchange buffers live ("cuda" for nccl, None = CPU for gloo)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    local_hist = np.ascontiguousarray(local_hist, dtype=np.int32)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local_hist
+    world = dist.get_world_size(group)
+    longest = max(s.count for s in shards)
+    buf = torch.zeros((longest, 256), dtype=torch.int32, device=device)
+    if local_hist.shape[0]:
+        buf[: local_hist.shape[0]] = torch.from_numpy(local_hist).to(buf.device)
+    out = torch.empty((world * longest, 256), dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    parts = out.cpu().numpy().reshape(world, longest, 256)
+    return np.concatenate([parts[s.rank, : s.count] for s in shards])

@@ -275,6 +275,14 @@ int cartb200_run_sequence_device(cartb200_ctx* ctx, const cartb200_sequence_opts
                                  const uint8_t* left_bgr_dev, const uint8_t* right_bgr_dev, uint8_t* planes_dev,
                                  int16_t* disparity_dev, void* stream);
 
+/* ---- source-side resize ------------------------------------------------------------------------------------------
+ * Replaces cv::cuda::resize(image, image, imageSize, 0, 0, cv::INTER_LINEAR, stream) on the CV_8UC3 frames of
+ * KITTIDataSource::getNextInternal (/root/reference/src/sources/kitti.cpp:166-169).  Device buffers, pitches in bytes,
+ * no context needed.  Bit-identical to oracle/stages.cpp orc_resize_bgr8; parity against OpenCV's kernel is unpinned
+ * (third-party cudawarping source, restated from the published algorithm). */
+int cartb200_resize_bgr8(const uint8_t* src_bgr, size_t src_pitch, int src_width, int src_height, uint8_t* dst_bgr,
+                         size_t dst_pitch, int dst_width, int dst_height, void* stream);
+
 /* ---- one sequence sharded over several GPUs (BASELINE.json configs[4]) ------------------
  * The superpixel chain is cut at every reset frame, so a shard that starts at id 1 or at a multiple of
  * sp_reset_iterations (opts->start_id) reproduces the unsharded labels.  The plane parameters of the histogram_peak

@@ -53,6 +53,7 @@ int orc_border_map(const uint16_t* labels, int W, int H, uint8_t* border, uint8_
 int orc_sp_relax(uint16_t* labels, int W, int H, int maxLabel, const uint8_t* ycrcb, const int16_t* deriv2,
                  int iterations, double directCost, double diagCost, double wCompact, double progressive, double wDisp,
                  double wImage, int32_t* borderCounts, int32_t* moved);
+int orc_resize_bgr8(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
 /* copyToShared simulation exposed for the tile-loader unit test (sanity_check.cu:58-65 idea):
  * fills out[(tileH+2*yPad) * (tileW+2*xPad)] int32 values and def flags for one block. */
 int orc_tile_i32(const int32_t* img, int W, int H, int bx, int by, int bdx, int bdy, int XB, int YB, int yPad, int xPad,

@@ -148,6 +148,15 @@ def depth(disp, Q):
     return out
 
 
+def resize_bgr8(img, dw, dh):
+    """cv::cuda::resize(..., INTER_LINEAR) on CV_8UC3 as restated in stages.cpp (parity unpinned)."""
+    img = _c(img, np.uint8)
+    sh, sw, _ = img.shape
+    out = np.empty((dh, dw, 3), np.uint8)
+    lib().orc_resize_bgr8(_p(img), sw, sh, _p(out), dw, dh)
+    return out
+
+
 def naive_derivative(disp, want_mask=False):
     disp = _c(disp, np.int16)
     H, W = disp.shape

@@ -478,4 +478,35 @@ int orc_depth(const int16_t* disp, int W, int H, const float* Q, float* xyz) {
     return 0;
 }
 
+// cv::cuda::resize(src, dst, size, 0, 0, cv::INTER_LINEAR) on CV_8UC3, as the KITTI source applies it when the configured
+// image size differs from the files' (/root/reference/src/sources/kitti.cpp:166-169).  The arithmetic lives in
+// opencv_contrib/cudawarping (third party, absent): PARITY UNPINNED - this restates its resize_linear kernel from the
+// published source as recollected: src = dst * (srcSize / dstSize) WITHOUT the half-pixel offset of the CPU cv::resize,
+// x1 = floor, x2 = x1 + 1 (reads clamped to the last row / column), four float weights, accumulation in float in the
+// order (y1,x1), (y1,x2), (y2,x1), (y2,x2), saturate_cast<uchar> = round to nearest even.  tests/test_oracle_cpu.py
+// bounds the distance to CPU cv2.resize (which samples half a pixel further).
+int orc_resize_bgr8(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh) {
+    const float fx = (float)(1.0 / ((double)dw / (double)sw)), fy = (float)(1.0 / ((double)dh / (double)sh));
+    for (int y = 0; y < dh; ++y)
+        for (int x = 0; x < dw; ++x) {
+            const float sx = (float)x * fx, sy = (float)y * fy;
+            const int x1 = (int)std::floor(sx), y1 = (int)std::floor(sy);
+            const int x2 = x1 + 1, y2 = y1 + 1;
+            const int x2r = x2 < sw - 1 ? x2 : sw - 1, y2r = y2 < sh - 1 ? y2 : sh - 1;
+            const int x1r = x1 < sw - 1 ? x1 : sw - 1, y1r = y1 < sh - 1 ? y1 : sh - 1;
+            const float w11 = ((float)x2 - sx) * ((float)y2 - sy), w12 = (sx - (float)x1) * ((float)y2 - sy);
+            const float w21 = ((float)x2 - sx) * (sy - (float)y1), w22 = (sx - (float)x1) * (sy - (float)y1);
+            for (int c = 0; c < 3; ++c) {
+                float out = 0.0f;
+                out = out + (float)src[((size_t)y1r * sw + x1r) * 3 + c] * w11;
+                out = out + (float)src[((size_t)y1r * sw + x2r) * 3 + c] * w12;
+                out = out + (float)src[((size_t)y2r * sw + x1r) * 3 + c] * w21;
+                out = out + (float)src[((size_t)y2r * sw + x2r) * 3 + c] * w22;
+                const float r = std::nearbyint(out);  // default rounding mode: to nearest even
+                dst[((size_t)y * dw + x) * 3 + c] = (uint8_t)(r < 0.0f ? 0.0f : (r > 255.0f ? 255.0f : r));
+            }
+        }
+    return 0;
+}
+
 }  // extern "C"

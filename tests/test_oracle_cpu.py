@@ -285,3 +285,23 @@ def test_depth_oracle_matches_opencv_cpu():
     y, x = 50, 160
     d = disp[y, x] / 16.0
     assert abs(o[y, x, 2] - 721.5 / (-d / 0.54 + 0.3)) < 1e-3
+
+
+def test_resize_oracle_properties():
+    """orc_resize_bgr8 restates cv::cuda::resize(INTER_LINEAR) (no half-pixel offset; parity against OpenCV-CUDA unpinned):
+    identity, constants, integer down-scaling = sub-sampling, and a bound against the CPU cv2.resize, which samples half a
+    source pixel further right / down."""
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    assert np.array_equal(po.resize_bgr8(img, 53, 37), img)
+    const = np.full((20, 30, 3), 77, np.uint8)
+    assert np.array_equal(po.resize_bgr8(const, 41, 17), np.full((17, 41, 3), 77, np.uint8))
+    big = rng.integers(0, 256, (40, 60, 3), dtype=np.uint8)
+    assert np.array_equal(po.resize_bgr8(big, 30, 20), big[::2, ::2])
+    # a smooth image: the two conventions differ by half a source pixel, i.e. by at most half the local gradient
+    yy, xx = np.mgrid[0:90, 0:160]
+    smooth = np.stack([(xx + yy) // 2, xx, yy * 2], -1).astype(np.uint8)
+    cv2 = pytest.importorskip("cv2")
+    ours = po.resize_bgr8(smooth, 120, 60).astype(int)
+    ref = cv2.resize(smooth, (120, 60), interpolation=cv2.INTER_LINEAR).astype(int)
+    assert np.abs(ours - ref).max() <= 2

@@ -10,7 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from cart_slam_b200.parallel import Shard, gather_to_rank0, plan_shards
+import cart_slam_b200 as cb
+from cart_slam_b200.parallel import Shard, allgather_histograms, gather_to_rank0, plan_shards
 
 
 def test_plan_cuts_only_at_reset_frames():
@@ -71,3 +72,34 @@ def test_gather_world2_gloo(tmp_path):
     assert full.shape == (n, H, W)
     for i in range(n):
         assert (full[i] == (i + 1) % 251).all()
+
+
+def _hist_worker(rank, world, port, n, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shards = plan_shards(n, world, 8)
+        me = shards[rank]
+        rng = np.random.default_rng(7)
+        all_hist = rng.integers(0, 5000, (n, 256)).astype(np.int32)  # every rank can regenerate the whole table
+        full = allgather_histograms(all_hist[me.frame_slice], shards)
+        assert np.array_equal(full, all_hist)
+        # the two-pass scheme: the schedule over the whole sequence, then the rank's own slice
+        opts = cb.SequenceOptions(pipeline=1, provider=1, update_interval=5, reset_interval=2, start_id=1)
+        params = cb.sequence_parameters(opts, full)
+        np.save(os.path.join(out_dir, f"params_{rank}.npy"), params[me.frame_slice])
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_histogram_exchange_and_parameter_schedule_world2_gloo(tmp_path):
+    """Phase 1 -> all-gather -> parameter schedule of the sharded runner with gloo on CPU: the ranks' slices concatenate
+    to the schedule a single process computes from the whole table."""
+    n = 43
+    mp.spawn(_hist_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
+    got = np.concatenate([np.load(str(tmp_path / f"params_{r}.npy")) for r in range(2)])
+    rng = np.random.default_rng(7)
+    all_hist = rng.integers(0, 5000, (n, 256)).astype(np.int32)
+    opts = cb.SequenceOptions(pipeline=1, provider=1, update_interval=5, reset_interval=2, start_id=1)
+    assert np.array_equal(got, cb.sequence_parameters(opts, all_hist))

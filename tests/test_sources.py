@@ -107,3 +107,62 @@ def test_pipeline_from_disk_equals_pipeline_from_memory(tmp_path):
     assert np.array_equal(disk["disparity"], mem["disparity"])
     assert np.array_equal(disk["planes"], mem["planes"])
     assert np.array_equal(disk["depth"], mem["depth"], equal_nan=True)
+
+
+def test_source_config_image_size_scales_q(tmp_path):
+    """"width" / "height" of a kitti source config = KITTIDataSource's imageSize argument: Q is scaled (kitti.cpp:137-148)."""
+    seq = SyntheticSequence(64, 32, 64, n_frames=1)
+    _write_sequence(str(tmp_path), [seq.frame(1)[:2]], seq=0)
+    native = host.open_source({"type": "kitti", "path": str(tmp_path), "sequence": 0})
+    scaled = host.open_source({"type": "kitti", "path": str(tmp_path), "sequence": 0, "width": 48, "height": 16})
+    assert native[:2] == (64, 32) and scaled[:2] == (48, 16)
+    assert np.isclose(scaled[2][0, 3], native[2][0, 3] * 48 / 64) and np.isclose(scaled[2][1, 3], native[2][1, 3] * 16 / 32)
+    assert np.isclose(scaled[2][2, 3], native[2][2, 3] * 48 / 64)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [(96, 48), (250, 131), (192, 96)])
+def test_resize_kernel_equals_oracle(size):
+    """cartb200_resize_bgr8 (the source's cv::cuda::resize replacement) against the oracle's restatement, bit for bit."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import cart_slam_b200 as cb
+    import pyoracle as po
+
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, (96, 192, 3), dtype=np.uint8)
+    got = cb.resize_bgr8(torch.from_numpy(img).cuda(), size[0], size[1]).cpu().numpy()
+    assert np.array_equal(got, po.resize_bgr8(img, size[0], size[1]))
+
+
+@pytest.mark.gpu
+def test_kitti_source_resizes_on_the_device(tmp_path):
+    """A source configured with another image size than the files' (KITTIDataSource's imageSize argument, kitti.cpp:166-169):
+    the modules see the resized frames, Q is scaled (kitti.cpp:137-148) - same planes as the pre-resized frames fed from
+    memory."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import pyoracle as po
+
+    W, H, D, n = 256, 128, 64, 3
+    seq = SyntheticSequence(W, H, D, n_frames=n, tint=True)
+    fr = [seq.frame(i + 1)[:2] for i in range(n)]
+    _write_sequence(str(tmp_path), fr, seq=0)
+    w2, h2 = 192, 96
+    modules = [{"type": "disparity", "num_disparities": D, "smoothing_radius": 2, "smoothing_iterations": 1},
+               {"type": "disparity_planeseg", "parameter_provider": {"type": "static", "horizontal_range_min": 1,
+                                                                      "horizontal_range_max": 30, "vertical_range_min": -3,
+                                                                      "vertical_range_max": 1}}]
+    disk = host.run_source({"type": "kitti", "path": str(tmp_path), "sequence": 0, "width": w2, "height": h2}, modules,
+                           max_frames=10, want_disparity=True)
+    assert disk["n"] == n and disk["planes"].shape[1:] == (h2, w2)
+    L = np.stack([po.resize_bgr8(f[0], w2, h2) for f in fr])
+    R = np.stack([po.resize_bgr8(f[1], w2, h2) for f in fr])
+    mem = host.run_config(modules, L, R, want_disparity=True)
+    assert np.array_equal(disk["disparity"], mem["disparity"]) and np.array_equal(disk["planes"], mem["planes"])
+    native = host.open_source({"type": "kitti", "path": str(tmp_path), "sequence": 0})
+    scaled = host.open_source({"type": "kitti", "path": str(tmp_path), "sequence": 0, "width": w2, "height": h2})
+    assert native[:2] == (W, H) and scaled[:2] == (w2, h2)
+    assert np.isclose(scaled[2][0, 3], native[2][0, 3] * w2 / W) and np.isclose(scaled[2][1, 3], native[2][1, 3] * h2 / H)
