@@ -53,11 +53,17 @@ struct StreamGuard {
     cudaStream_t s = nullptr;
     StreamGuard() : ps(streamPool().take()), s(ps.s) {}
     ~StreamGuard() { streamPool().give(ps); }  // every module synchronises the stream before it returns
-    // polling with yield: as fast as the default spin-wait when the host is idle, but a waiting module thread gives its
-    // core to whoever is runnable (the PNG decoders) - a blocking-sync event costs ~100 us of wake-up latency per module call
+    // Short waits (one frame in flight: a module's kernels take 50-300 us) are polled - a blocking-sync event costs ~100 us
+    // of wake-up latency per module call.  With a dozen frames in flight the waits are long and dozens of threads polling
+    // cudaStreamQuery fight over the driver's context lock with the threads that launch kernels, so after a bounded
+    // number of polls the thread blocks on the stream's event instead.
     void sync() {
-        cudaError_t e;
-        while ((e = cudaStreamQuery(s)) == cudaErrorNotReady) std::this_thread::yield();
+        cudaError_t e = cudaErrorNotReady;
+        for (int i = 0; i < 48 && (e = cudaStreamQuery(s)) == cudaErrorNotReady; ++i) std::this_thread::yield();
+        if (e == cudaErrorNotReady) {
+            e = cudaEventRecord(ps.done, s);
+            if (e == cudaSuccess) e = cudaEventSynchronize(ps.done);
+        }
         if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e));
     }
 };
