@@ -7,8 +7,10 @@ A "step" is one pass of the hot path over one KITTI-shaped synthetic stereo sequ
          (cart_slam_b200.parallel.plan_shards).  The histogram_peak parameters come from a running histogram that
          crosses the shard boundaries, hence the two-pass scheme of SURVEY.md section 8(e): phase 1 per shard ->
          all-gather of the per-frame histograms (256 int32 per frame) -> the reference's parameter schedule on the CPU
-         -> phase 2 per shard -> gather of the plane labels to rank 0.  The result equals the unsharded run bit for bit
-         (tests/test_sharded_sequence.py).  Total work is fixed: "strong" scaling; the gather is timed separately.
+         -> phase 2 per shard -> gather of the plane labels to rank 0 (device).  The result equals the unsharded run bit
+         for bit (tests/test_sharded_sequence.py).  Total work is fixed: "strong" scaling; the gather is timed separately.
+         `e2e` at N > 1: every rank uploads its shard from pinned host memory inside phase 1 and reads its own shard of
+         the planes back into its own pinned host buffer, next to the device gather.
 
   value  : frames/s with the sequence already resident in HBM (cartb200_run_sequence_device)
   e2e    : frames/s through the C ABI call that takes HOST buffers (cartb200_run_sequence_host):
@@ -432,7 +434,8 @@ def main():
         hostR = torch.from_numpy(R).pin_memory()
     devL, devR = hostL.cuda(non_blocking=True), hostR.cuda(non_blocking=True)
     planes_dev = torch.zeros((max_count, H, W), dtype=torch.uint8, device="cuda")  # padded to the largest shard for the gather
-    planes_host = torch.empty((total if rank == 0 else 1, H, W), dtype=torch.uint8).pin_memory()
+    planes_host = torch.empty((1 if sharded else total, H, W), dtype=torch.uint8).pin_memory()
+    shard_host = torch.empty((max(n, 1), H, W), dtype=torch.uint8).pin_memory() if sharded else None
     torch.cuda.synchronize()
 
     cfg = cb.Config(W, H, max_batch=args.batch, num_disparities=D, min_disparity=MIN_DISP, paths=n_paths, smoothing_radius=2,
@@ -470,12 +473,10 @@ def main():
     def gather(to_host):
         if not sharded:
             return
+        if to_host:  # end to end: every rank reads its own shard of the result into its own pinned host buffer (N PCIe
+            # links in parallel); the gather of BASELINE configs[4] stays on the device
+            shard_host[:n].copy_(planes_dev[:n], non_blocking=True)
         dist.gather(planes_dev, gather_buf, dst=0)  # the final result gather (padded shards)
-        if to_host and rank == 0:  # the job's result lands in rank 0's host memory
-            o = 0
-            for r in range(world):
-                planes_host[o:o + shards[r].count].copy_(gather_buf[r][:shards[r].count], non_blocking=True)
-                o += shards[r].count
 
     def barrier():
         if world > 1:
