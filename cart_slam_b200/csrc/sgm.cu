@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) gray_census_kernel(ImgBatch<const uint8_t
                                                           uint8_t* __restrict__ grayL, size_t grayPitch,
                                                           uint32_t* __restrict__ cenL, uint32_t* __restrict__ cenR,
                                                           size_t cenRowWords, int cenMargin, int minDisp, int W, int H) {
-    __shared__ uint8_t g[kCenTH + 6][kCenTW + 8];
+    __shared__ __align__(16) uint8_t g[kCenTH + 6][kCenTW + 8];
     const int f = blockIdx.z >> 1, side = blockIdx.z & 1;
     Img<const uint8_t> src = side ? right.frame(f) : left.frame(f);
     const int x0 = blockIdx.x * kCenTW - 4, y0 = blockIdx.y * kCenTH - 3;
@@ -48,21 +48,64 @@ __global__ void __launch_bounds__(256) gray_census_kernel(ImgBatch<const uint8_t
     // out-of-image columns as the 0 the specification asks for; the RIGHT census is stored shifted by
     // min_disparity: element (margin + i) holds cR[i - minDisp], i.e. the word for (x, d) is at x - d.
     uint32_t* out = (side ? cenR : cenL) + (size_t)f * H * cenRowWords + cenMargin + (side ? minDisp : 0);
-    for (int i = threadIdx.x; i < kCenTH * kCenTW; i += blockDim.x) {
-        const int ty = i / kCenTW, tx = i % kCenTW;
+    // Four horizontally adjacent pixels per thread: the 31 comparisons act on packed bytes (a > b per byte in four
+    // logic / add operations on the whole word), the gray rows come as aligned 32-bit words (21 shared loads instead of
+    // 248 byte loads), and the bits are collected bytewise - accumulator k gathers bits 8k .. 8k+7 of all four pixels -
+    // and transposed into the four census words at the end.  Comparison j (the specification's order) is bit 30 - j.
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(&g[0][0]);
+    constexpr int kRowWords = (kCenTW + 8) / 4;  // 32
+    auto gt4 = [](uint32_t a, uint32_t b) {      // bit 7 of every byte: a > b (unsigned bytes)
+        const uint32_t t = (b & 0x7F7F7F7Fu) + (~a & 0x7F7F7F7Fu);  // low 7 bits of (b + ~a): carry into bit 7 iff b7 > a7 there
+        // a > b  <=>  not (b >= a).  Per byte: ge = carry of b + ~a + 1; composed from the high bits and t's bit 7
+        // (lop3 0xb2 in nvcc's own expansion of __vcmpgtu4): majority(b, ~a, t) gives the carry out, i.e. b > a ... we
+        // need a > b, so the operands are swapped at the call sites below
+        return ((b & ~a) | ((b | ~a) & t));  // bit 7 per byte = carry out of b + ~a = (b > a)
+    };
+    for (int i = threadIdx.x; i < kCenTH * (kCenTW / 4); i += blockDim.x) {
+        const int ty = i / (kCenTW / 4), q = i % (kCenTW / 4);
+        const int tx = 4 * q;
         const int x = x0 + 4 + tx, y = y0 + 3 + ty;
         if (x >= W || y >= H) continue;
-        uint32_t c = 0;
-        if (x >= 4 && x < W - 4 && y >= 3 && y < H - 3) {
-            const int cx = tx + 4, cy = ty + 3;
+        const int cy = ty + 3;
+        // words of the 7 rows: columns tx .. tx + 11 of the staged tile = image columns x - 4 .. x + 7
+        uint32_t w[7][3];
 #pragma unroll
-            for (int dy = -3; dy < 0; ++dy)
+        for (int r = 0; r < 7; ++r)
 #pragma unroll
-                for (int dx = -4; dx <= 4; ++dx) c = (c << 1) | (uint32_t)(g[cy + dy][cx + dx] > g[cy - dy][cx - dx]);
+            for (int k = 0; k < 3; ++k) w[r][k] = gw[(cy - 3 + r) * kRowWords + q + k];
+        auto bytes4 = [&](int r, int dx) {  // gray values of the four pixels at row offset r - 3, column offset dx
+            const int o = dx + 4;           // 0 .. 8
+            const uint32_t lo = w[r][o >> 2], hi = w[r][(o >> 2) + ((o & 3) ? 1 : 0)];
+            switch (o & 3) {
+                case 0: return lo;
+                case 1: return __byte_perm(lo, hi, 0x4321);
+                case 2: return __byte_perm(lo, hi, 0x5432);
+                default: return __byte_perm(lo, hi, 0x6543);
+            }
+        };
+        uint32_t T[4] = {0, 0, 0, 0};
+        // comparison j: j < 27: dy = -3 + j / 9, dx = -4 + j % 9 (rows 3 + dy against 3 - dy); else dy = 0, dx = -4 + (j - 27)
 #pragma unroll
-            for (int dx = -4; dx < 0; ++dx) c = (c << 1) | (uint32_t)(g[cy][cx + dx] > g[cy][cx - dx]);
+        for (int p = 0; p < 31; ++p) {  // ascending bit position p: within a byte the first processed bit ends at its bit 0
+            const int j = 30 - p;
+            const int dy = j < 27 ? -3 + j / 9 : 0, dx = j < 27 ? -4 + j % 9 : -4 + (j - 27);
+            const uint32_t a = bytes4(3 + dy, dx), b = bytes4(3 - dy, -dx);
+            const uint32_t r = gt4(b, a);  // bit 7 per byte: a > b
+            T[p >> 3] = (T[p >> 3] >> 1) | (r & 0x80808080u);
         }
-        out[(size_t)y * cenRowWords + x] = c;
+        T[3] >>= 1;  // the top byte only received 7 bits
+        // transpose: census word of pixel k = byte k of T[0], T[1], T[2], T[3]
+        const uint32_t lo01 = __byte_perm(T[0], T[1], 0x5140), hi01 = __byte_perm(T[0], T[1], 0x7362);  // (T0.0 T1.0 T0.1 T1.1), (T0.2 T1.2 T0.3 T1.3)
+        const uint32_t lo23 = __byte_perm(T[2], T[3], 0x5140), hi23 = __byte_perm(T[2], T[3], 0x7362);
+        const uint32_t c[4] = {__byte_perm(lo01, lo23, 0x5410), __byte_perm(lo01, lo23, 0x7632), __byte_perm(hi01, hi23, 0x5410),
+                               __byte_perm(hi01, hi23, 0x7632)};
+        const bool rowOk = y >= 3 && y < H - 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xk = x + k;
+            if (xk >= W) break;
+            out[(size_t)y * cenRowWords + xk] = (rowOk && xk >= 4 && xk < W - 4) ? c[k] : 0u;
+        }
     }
 }
 
