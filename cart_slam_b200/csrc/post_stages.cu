@@ -59,6 +59,45 @@ __global__ void __launch_bounds__(256) interpolate_kernel(ImgBatch<const int16_t
     __syncthreads();
     const unsigned minCount = (unsigned)(radius * radius + 1);
     for (int it = 0; it < iterations; ++it) {
+        if (radius == 2) {
+            // 3x3 window (the shipped configurations): four adjacent pixels per thread share their 3 x 6 window values,
+            // read as 32-bit pairs (the tile stride 66 is even and the group starts at an even element)
+            for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+                const int ly = i >> 4, lx = (i & 15) * 4;
+                if (bx * 64 + lx >= W || by * 64 + ly >= H) continue;
+                int sum[4] = {0, 0, 0, 0};
+                unsigned cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    const uint32_t* rp = reinterpret_cast<const uint32_t*>(cur + (ly + l) * S + lx);  // columns lx-1 .. lx+4
+                    int v[6];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const uint32_t w2 = rp[k];
+                        v[2 * k] = (int)(int16_t)(w2 & 0xFFFFu);
+                        v[2 * k + 1] = (int)(int16_t)(w2 >> 16);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const bool ok = v[k] > minD && v[k] < maxD;
+                        const int m = ok ? v[k] : 0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (k >= q && k <= q + 2) {
+                                sum[q] += m;
+                                cnt[q] += ok ? 1u : 0u;
+                            }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (bx * 64 + lx + q >= W) break;
+                    int16_t res = kInvalid;
+                    if (cnt[q] > minCount) res = (int16_t)__umulhi((unsigned)sum[q], recipM[cnt[q]]);
+                    nxt[(ly + 1) * S + lx + q + 1] = res;
+                }
+            }
+        } else
         for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
             const int ly = i >> 6, lx = i & 63;
             if (bx * 64 + lx >= W || by * 64 + ly >= H) continue;
