@@ -81,12 +81,85 @@ int wta_post_batch(cartb200_ctx* c, int n, ImgBatch<int16_t> out, cudaStream_t s
                                    c->cfg.smoothing_radius, c->cfg.smoothing_iterations, c->cfg.min_disparity * 16, c->W, s);
 }
 
+// The SGM scratch of a context is indexed by frame; a FrameWindow makes the stage launchers work on frames [f0, ...)
+// by advancing the base pointers for its lifetime (launches capture the pointers by value).
+struct FrameWindow {
+    cartb200_ctx* c;
+    uint8_t *grayL, *grayR, *volumes;
+    uint32_t *censusL, *censusR, *wtaR;
+    uint16_t *wtaL, *medL, *medR;
+    FrameWindow(cartb200_ctx* ctx, int f0)
+        : c(ctx), grayL(ctx->grayL), grayR(ctx->grayR), volumes(ctx->volumes), censusL(ctx->censusL), censusR(ctx->censusR),
+          wtaR(ctx->wtaR), wtaL(ctx->wtaL), medL(ctx->medL), medR(ctx->medR) {
+        const size_t f = (size_t)f0, H = (size_t)c->H;
+        c->grayL += f * H * c->grayPitch;
+        if (c->grayR) c->grayR += f * H * c->grayPitch;
+        c->volumes += f * c->volFrameStride;
+        c->censusL += f * H * c->cenRowWords;
+        c->censusR += f * H * c->cenRowWords;
+        c->wtaR += f * H * c->rkPitch;
+        c->wtaL += f * H * (c->dispPitch / 2);
+        c->medL += f * H * (c->dispPitch / 2);
+        if (c->medR) c->medR += f * H * (c->dispPitch / 2);
+    }
+    ~FrameWindow() {
+        c->grayL = grayL, c->grayR = grayR, c->volumes = volumes, c->censusL = censusL, c->censusR = censusR;
+        c->wtaR = wtaR, c->wtaL = wtaL, c->medL = medL, c->medR = medR;
+    }
+};
+
+// Frames per slice of a batch (0 = unsliced).  Aggregation is bound by the XU / ALU pipes and uses 55 % of the HBM
+// bandwidth, the winner-takes-all pass is bound by HBM reads: with the batch cut into slices the WTA pass of slice i
+// shares the SMs with the aggregation of slice i + 1.  CARTB200_SGM_SLICE (tuning aid) overrides the default.
+static int sgmSliceFrames() {
+    const char* e = getenv("CARTB200_SGM_SLICE");  // read per batch: a sweep can change it inside one process
+    return e ? atoi(e) : 0;
+}
+
 int disparity_batch(cartb200_ctx* c, int n, ImgBatch<const uint8_t> left, ImgBatch<const uint8_t> right, ImgBatch<int16_t> disp,
                     cudaStream_t s) {
     int rc;
     if ((rc = launch_gray_census(c, n, left, right, s))) return rc;
-    if ((rc = launch_aggregate(c, n, s))) return rc;
-    return wta_post_batch(c, n, disp, s);
+    // a slice is a whole number of inner groups of a two-level batch, so that it is a batch of the same kind
+    const int unit = disp.inner > 0 ? disp.inner : 1;
+    int slice = sgmSliceFrames();
+    slice = slice > 0 ? std::max(unit, slice / unit * unit) : 0;
+    if (slice <= 0 || slice >= n) {
+        if ((rc = launch_aggregate(c, n, s))) return rc;
+        return wta_post_batch(c, n, disp, s);
+    }
+    if (!c->wtaStream) {
+        int lo = 0, hi = 0;
+        CB_CHECK_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        // high priority: the CTAs of a WTA pass take the slots that free up first, so that slice i is finished while the
+        // aggregation of slice i + 1 is still running
+        CB_CHECK_CUDA(c, cudaStreamCreateWithPriority(&c->wtaStream, cudaStreamNonBlocking, hi));
+        CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&c->evSliceAgg, cudaEventDisableTiming));
+        CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&c->evSliceWta, cudaEventDisableTiming));
+    }
+    auto slices = [&]() -> int {
+        for (int f0 = 0; f0 < n; f0 += slice) {
+            const int m = std::min(slice, n - f0);
+            FrameWindow w(c, f0);
+            if ((rc = launch_aggregate(c, m, s))) return rc;
+            CB_CHECK_CUDA(c, cudaEventRecord(c->evSliceAgg, s));
+            CB_CHECK_CUDA(c, cudaStreamWaitEvent(c->wtaStream, c->evSliceAgg, 0));
+            ImgBatch<int16_t> d = disp;
+            d.data = (int16_t*)((char*)disp.data + (disp.inner > 0 ? (size_t)(f0 / disp.inner) * disp.outerStride
+                                                                   : (size_t)f0 * disp.frameStride));
+            if ((rc = wta_post_batch(c, m, d, c->wtaStream))) return rc;
+        }
+        return CARTB200_OK;
+    };
+    rc = slices();
+    // join the second stream on every path out of here: nothing may still write `disp` after the caller's stream is done
+    if (cudaEventRecord(c->evSliceWta, c->wtaStream) != cudaSuccess || cudaStreamWaitEvent(s, c->evSliceWta, 0) != cudaSuccess) {
+        if (rc == CARTB200_OK) {
+            c->err = "disparity_batch: joining the WTA stream failed";
+            rc = CARTB200_E_CUDA;
+        }
+    }
+    return rc;
 }
 }  // namespace cb
 
@@ -318,6 +391,9 @@ void cartb200_destroy(cartb200_ctx* c) {
         if (c->aggJoin[i]) cudaEventDestroy(c->aggJoin[i]);
     }
     if (c->aggFork) cudaEventDestroy(c->aggFork);
+    if (c->wtaStream) cudaStreamDestroy(c->wtaStream);
+    if (c->evSliceAgg) cudaEventDestroy(c->evSliceAgg);
+    if (c->evSliceWta) cudaEventDestroy(c->evSliceWta);
     cudaFree(c->grayL);
     cudaFree(c->grayR);
     cudaFree(c->censusL);
@@ -420,10 +496,19 @@ int cartb200_sgm_wta_post(cartb200_ctx* c, int n, int16_t* d, size_t pitch, size
 
 int cartb200_disparity(cartb200_ctx* c, int n, const uint8_t* l, const uint8_t* r, size_t pitch, size_t fstride,
                        int16_t* d, size_t dpitch, size_t dfstride, void* stream) {
-    int rc;
-    if ((rc = cartb200_sgm_gray_census(c, n, l, r, pitch, fstride, stream))) return rc;
-    if ((rc = cartb200_sgm_aggregate(c, n, stream))) return rc;
-    return cartb200_sgm_wta_post(c, n, d, dpitch, dfstride, stream);
+    int rc = checkBatch(c, n);
+    if (rc) return rc;
+    if ((rc = checkSgm(c))) return rc;
+    if (!l || !r || pitch < (size_t)c->W * 3) {
+        c->err = "gray_census: bad image arguments";
+        return CARTB200_E_ARG;
+    }
+    if (!d || dpitch < (size_t)c->W * 2) {
+        c->err = "wta_post: bad image arguments";
+        return CARTB200_E_ARG;
+    }
+    return cb::disparity_batch(c, n, ImgBatch<const uint8_t>{l, pitch, fstride}, ImgBatch<const uint8_t>{r, pitch, fstride},
+                               ImgBatch<int16_t>{d, dpitch, dfstride}, (cudaStream_t)stream);
 }
 
 int cartb200_sgm_intermediate(cartb200_ctx* c, int which, const void** ptr, size_t* pitch, size_t* fstride) {

@@ -103,6 +103,10 @@ struct cartb200_ctx {
     // that the last, partially filled wave of one launch is filled by the next (lazy)
     cudaStream_t aggStream[2] = {nullptr, nullptr};
     cudaEvent_t aggFork = nullptr, aggJoin[2] = {nullptr, nullptr};
+    // sliced SGM (disparity_batch): the winner-takes-all pass of slice i runs on this stream beside the aggregation of
+    // slice i + 1 (lazy)
+    cudaStream_t wtaStream = nullptr;
+    cudaEvent_t evSliceAgg = nullptr, evSliceWta = nullptr;
     // sequence runner scratch (lazy)
     void* seq = nullptr;
 };

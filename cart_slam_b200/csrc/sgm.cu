@@ -404,6 +404,126 @@ __global__ void __launch_bounds__(kHorizThreads, MINB) aggregate_horizontal_kern
         horizontal_body<D, -1, U, PF>(a, vol);
 }
 
+// ---- horizontal, 32 disparities per lane -------------------------------------------------------------
+// Experiment (CARTB200_HORIZ_VARIANT=6): a lane owns 32 disparities as 16 x u16x2 in the interleaved order (d_i, d_i+16),
+// a pixel is spread over D/32 lanes: 2 neighbour + log2(D/32) group-minimum shuffles per 32 cells instead of 2 + log2(D/16)
+// per 16 (D = 128: 2 instead of 5 per 16 cells) - POPC and SHFL share the MIO queue.  64-thread CTAs.  Measured on B200
+// (64-frame batch, bit-identical volumes): 1.32 ms per path at 80 registers / 24 warps per SM, 1.37-1.43 ms at 96-128
+// registers / 16-20 warps, against 1.17 ms for the 16-per-lane kernel at 64 registers / 32 warps: the resident warps the
+// wider lane costs matter more than the shuffles it saves.  Kept for reproduction, not used.
+template <int NR, int LPP>
+__device__ __forceinline__ uint32_t dp_step_w(uint32_t (&dp)[NR], const uint32_t (&cost)[2 * NR], uint32_t K, uint32_t maskUp,
+                                              uint32_t maskDn, uint32_t negP1v, uint32_t P2v) {
+    uint32_t qp[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) qp[i] = dp[i] + K;
+    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, qp[NR - 1], 1) | maskUp;
+    const uint32_t dn = __shfl_down_sync(0xFFFFFFFFu, qp[0], 1) | maskDn;
+    const uint32_t lower0 = __byte_perm(up, qp[NR - 1], 0x5432);
+    const uint32_t upperL = __byte_perm(qp[0], dn, 0x5432);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        const uint32_t qc = __viaddmin_u16x2(qp[i], negP1v, P2v);
+        dp[i] = __vimin3_u16x2(i == 0 ? lower0 : qp[i - 1], i == NR - 1 ? upperL : qp[i + 1], qc) + cost[i] + (cost[i + NR] << 16);
+    }
+    uint32_t mn = dp[0];
+#pragma unroll
+    for (int i = 1; i + 1 < NR; i += 2) mn = __vimin3_u16x2(mn, dp[i], dp[i + 1]);
+    if ((NR & 1) == 0) mn = __vminu2(mn, dp[NR - 1]);
+    return __vminu2(mn, __byte_perm(mn, 0, 0x1032));  // (min, min)
+}
+
+constexpr int kHoriz32Threads = 64;
+template <int D, int DX, int U>
+__device__ __forceinline__ void horizontal_body32(const PathArgs& a, uint8_t* __restrict__ volBase) {
+    constexpr int DL = 32, NR = 16;
+    constexpr int LPP = D / DL;
+    constexpr int GPB = kHoriz32Threads / LPP;
+    const int lane = threadIdx.x % LPP;
+    const int group = threadIdx.x / LPP;
+    const int f = blockIdx.y;
+    const int W = a.W;
+    const int line = blockIdx.x * GPB + group;
+    const int y = line < a.H ? line : a.H - 1;
+    const uint32_t* cl = a.cenL + (size_t)f * a.cenFrameStride + (size_t)y * a.cenStride + a.cenMargin;
+    const uint32_t* cr = a.cenR + (size_t)f * a.cenFrameStride + (size_t)y * a.cenStride + a.cenMargin - DL * lane - DL;
+    uint8_t* vrow = volBase + (size_t)f * a.volFrameStride + (size_t)y * W * D + DL * lane;
+    const uint32_t maskUp = lane == 0 ? kSentinelHi : 0u, maskDn = lane == LPP - 1 ? kSentinelLo : 0u;
+    const int nChunks = (W + U - 1) / U;
+    uint32_t P1v, P2v, negP1v;
+    asm volatile("mov.u32 %0, %1;" : "=r"(P1v) : "r"(a.P1v));
+    asm volatile("mov.u32 %0, %1;" : "=r"(P2v) : "r"(a.P2v));
+    asm volatile("mov.u32 %0, %1;" : "=r"(negP1v) : "r"(a.negP1v));
+    uint32_t dp[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) dp[i] = 0;
+    uint32_t K = P1v;
+    uint32_t S[DL + U];  // S[k] = shifted right census word (x0 - DL*lane - DL + k)
+    uint32_t Lw[U];
+    {
+        const int x0 = DX > 0 ? 0 : U * (nChunks - 1);
+        load_words<DL>(DX > 0 ? S : S + U, cr + x0 + (DX > 0 ? 0 : U));
+    }
+    for (int c = 0; c < nChunks; ++c) {
+        const int x0 = DX > 0 ? U * c : U * (nChunks - 1 - c);
+        load_words<U>(Lw, cl + x0);
+        load_words<U>(DX > 0 ? S + DL : S, cr + x0 + (DX > 0 ? DL : 0));
+        if (a.pfPixels > 0) {
+            const int xp = DX > 0 ? x0 + a.pfPixels : x0 - a.pfPixels;
+            if (DX > 0 ? xp < W : xp >= 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(cl + xp));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(cr + xp + (DX > 0 ? DL : 0)));
+            }
+        }
+        uint8_t* vchunk = vrow + (size_t)x0 * D;
+        auto step = [&](int sidx) {
+            uint32_t cost[DL];
+#pragma unroll
+            for (int k = 0; k < DL; ++k) cost[k] = __popc(Lw[sidx] ^ S[DL + sidx - k]);
+            K = P1v - group_min2<LPP>(dp_step_w<NR, LPP>(dp, cost, K, maskUp, maskDn, negP1v, P2v));
+            // registers (d_i, d_i+16) -> 32 bytes d0 .. d31 (two 16-byte stores)
+            uint32_t lo[4], hi[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t A = __byte_perm(dp[4 * g], dp[4 * g + 1], 0x6420);      // d d+16 d+1 d+17
+                const uint32_t B = __byte_perm(dp[4 * g + 2], dp[4 * g + 3], 0x6420);  // d+2 d+18 d+3 d+19
+                lo[g] = __byte_perm(A, B, 0x6420);
+                hi[g] = __byte_perm(A, B, 0x7531);
+            }
+            uint8_t* dst = vchunk + sidx * D;
+            __stcs(reinterpret_cast<uint4*>(dst), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            __stcs(reinterpret_cast<uint4*>(dst + 16), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+        };
+        if (x0 + U <= W) {
+#pragma unroll
+            for (int t = 0; t < U; ++t) step(DX > 0 ? t : U - 1 - t);
+        } else {
+#pragma unroll
+            for (int t = 0; t < U; ++t) {
+                const int sidx = DX > 0 ? t : U - 1 - t;
+                if (x0 + sidx < W) step(sidx);
+            }
+        }
+        if (DX > 0) {
+#pragma unroll
+            for (int k = 0; k < DL; ++k) S[k] = S[k + U];
+        } else {
+#pragma unroll
+            for (int k = DL - 1; k >= 0; --k) S[k + U] = S[k];
+        }
+    }
+}
+
+template <int D, int U, int MINB>
+__global__ void __launch_bounds__(kHoriz32Threads, MINB) aggregate_horizontal32_kernel(PathArgs a, int dirFirst, int both) {
+    const int dir = both ? (blockIdx.z == 0 ? 1 : -1) : dirFirst;
+    uint8_t* vol = (both && blockIdx.z == 1) ? a.vol2 : a.vol;
+    if (dir > 0)
+        horizontal_body32<D, 1, U>(a, vol);
+    else
+        horizontal_body32<D, -1, U>(a, vol);
+}
+
 // ---- vertical -------------------------------------------------------------------------------------
 template <int D, int MINB>
 __global__ void __launch_bounds__(128, MINB) aggregate_vertical_kernel(PathArgs a, int dirFirst, int both) {
@@ -658,11 +778,18 @@ static void launch_paths_D(cartb200_ctx* c, PathArgs a, int n, int p0, int p1, c
             // measured on B200 (64-frame batch, profiles/r01n_aggregate_variant_sweep.txt): with the census rows
             // prefetched into L2, the register prefetch of the next chunk is not needed any more and 64 registers /
             // 8 CTAs per SM beat the 96-register prefetching variant by 2.7 %.  CARTB200_HORIZ_VARIANT (tuning aid)
-            // selects the older shapes.
-            static const int variant = getenv("CARTB200_HORIZ_VARIANT") ? atoi(getenv("CARTB200_HORIZ_VARIANT")) : 0;
+            // selects the other measured shapes (profiles/r02v_aggregate_variant_sweep.json): 1, 2 = the older ones,
+            // 6 = 32 disparities per lane (80 registers, 24 warps/SM: 12 % slower), 7 = 4-pixel window refills at
+            // 56 registers / 9 CTAs (3 % slower).
+            const int variant = getenv("CARTB200_HORIZ_VARIANT") ? atoi(getenv("CARTB200_HORIZ_VARIANT")) : 0;
+            if (variant == 6) {  // 32 disparities per lane (measured and rejected, see horizontal_body32)
+                dim3 g32(ceilDiv(a.H, kHoriz32Threads / (D / 32)), n, pair ? 2 : 1);
+                aggregate_horizontal32_kernel<D, 4, 12><<<g32, kHoriz32Threads, 0, s>>>(a, a.dx, pair ? 1 : 0);
+            } else
             switch (variant) {  // (pixels per window refill, register prefetch, minimum CTAs per SM)
                 case 1: aggregate_horizontal_kernel<D, 8, true, 5><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0); break;
                 case 2: aggregate_horizontal_kernel<D, 8, false, 6><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0); break;
+                case 7: aggregate_horizontal_kernel<D, 4, false, 9><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0); break;
                 default: aggregate_horizontal_kernel<D, kHorizU, false, 8><<<grid, kHorizThreads, 0, s>>>(a, a.dx, pair ? 1 : 0);
             }
         } else if (a.dx == 0) {

@@ -1,5 +1,6 @@
 """Parity of the CUDA path (through the C ABI) against the CPU oracle, on a real GPU.
 Integer stages: bit-exact.  Superpixel labels: >= 99.9 % per-pixel agreement (fp64 costs, CUDA log vs libm)."""
+import os
 import numpy as np
 import pytest
 
@@ -80,6 +81,14 @@ def test_disparity_batch_equals_single_and_is_repeatable(gpu):
             assert np.array_equal(one[0], a[f])
         o = po.interpolate(po.sgm_compute(L[2], R[2], D), 2, 1, 64, W)
         assert np.array_equal(a[2], o)
+        # sliced SGM (tuning aid CARTB200_SGM_SLICE: WTA of slice i beside the aggregation of slice i + 1 on a second
+        # stream, frame windows into the context's scratch): same bits for every slice size, ragged last slice included
+        try:
+            for sl in ("1", "2", "3"):
+                os.environ["CARTB200_SGM_SLICE"] = sl
+                assert np.array_equal(host(ctx.disparity(dev(L), dev(R))), a), f"slice {sl}"
+        finally:
+            os.environ.pop("CARTB200_SGM_SLICE", None)
 
 
 @pytest.mark.parametrize("radius,iters", [(2, 1), (3, 1), (3, 3), (4, 2)])
