@@ -34,6 +34,9 @@ struct SeqScratch {
     int32_t* paramsHost = nullptr;  // pinned [n][4]
     cudaStream_t copyStream = nullptr;
     cudaStream_t spStream = nullptr;       // superpixel relaxation runs beside the SGM stages of the next batch
+    static constexpr int kSpGroups = 8;    // the lock-stepped chunks advance as up to kSpGroups groups on streams of their own
+    cudaStream_t spStreamX[kSpGroups - 1] = {};  // groups 1.. (group 0 runs on spStream)
+    cudaEvent_t evSpFork = nullptr, evSpJoin[kSpGroups - 1] = {};
     std::vector<cudaEvent_t> evBatch;      // batch k: disparity + derivative done (recorded on the main stream)
     cudaEvent_t evStart = nullptr, evSpDone = nullptr;
     cudaEvent_t evIn[2] = {nullptr, nullptr};
@@ -424,6 +427,11 @@ void cartb200_destroy(cartb200_ctx* c) {
         cudaFreeHost(q->paramsHost);
         if (q->copyStream) cudaStreamDestroy(q->copyStream);
         if (q->spStream) cudaStreamDestroy(q->spStream);
+        for (auto& st : q->spStreamX)
+            if (st) cudaStreamDestroy(st);
+        if (q->evSpFork) cudaEventDestroy(q->evSpFork);
+        for (auto& e : q->evSpJoin)
+            if (e) cudaEventDestroy(e);
         for (auto& e : q->evBatch) cudaEventDestroy(e);
         if (q->evStart) cudaEventDestroy(q->evStart);
         if (q->evSpDone) cudaEventDestroy(q->evSpDone);
@@ -939,6 +947,9 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
             CB_CHECK_CUDA(c, cudaStreamCreateWithPriority(&q->spStream, cudaStreamNonBlocking, hi));
+            for (auto& st : q->spStreamX) CB_CHECK_CUDA(c, cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
+            CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&q->evSpFork, cudaEventDisableTiming));
+            for (auto& e : q->evSpJoin) CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
         CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&q->evStart, cudaEventDisableTiming));
         CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&q->evSpDone, cudaEventDisableTiming));
@@ -954,6 +965,8 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
         ~JoinOnError() {
             if (ok) return;
             if (q->spStream) cudaStreamSynchronize(q->spStream);
+            for (auto& st : q->spStreamX)
+                if (st) cudaStreamSynchronize(st);
             if (q->copyStream) cudaStreamSynchronize(q->copyStream);
         }
     } joinGuard{q};
@@ -1199,27 +1212,58 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
         CB_CHECK_CUDA(c, cudaStreamWaitEvent(spS, q->evBatch[bi], 0));
         ImgBatch<uint8_t> pB = seqBatch(planesDev, pxFrame);
         pB.pitch = W;
-        // superpixels, one step at a time: reset + iteration schedule (superpixels.cu:93-113)
+        // superpixels, one step at a time: reset + iteration schedule (superpixels.cu:93-113).  The chunks of a batch are
+        // independent chains: they are advanced as G groups on G streams, so that the partially filled last wave of one
+        // group's relaxation launch (16 frames = 1920 tiles on 740 resident CTAs: 2.6 waves) is filled by the launches
+        // of the other groups instead of idling.  CARTB200_SP_SPLIT = G (1 keeps one stream; measured: profiles/r02w_*).
+        static const int spGroups = std::max(1, std::min<int>(SeqScratch::kSpGroups, getenv("CARTB200_SP_SPLIT") ? atoi(getenv("CARTB200_SP_SPLIT")) : 2));
+        // (the one step that gives frame id 1 its own iteration count keeps the single stream)
+        const bool hasIdOne = bt.idA <= 1 && 1 < bt.idA + k && !(bt.st == 0 && bt.idA == 1);
+        const int G = hasIdOne ? 1 : std::max(1, std::min(spGroups, nb / 2));
+        int gOff[SeqScratch::kSpGroups + 1];
+        for (int g = 0; g <= G; ++g) gOff[g] = (int)((long)nb * g / G);
+        auto gStream = [&](int g) { return g == 0 ? spS : q->spStreamX[g - 1]; };
+        const bool split = G > 1;
+        if (split) {
+            CB_CHECK_CUDA(c, cudaEventRecord(q->evSpFork, spS));
+            for (int g = 1; g < G; ++g) CB_CHECK_CUDA(c, cudaStreamWaitEvent(gStream(g), q->evSpFork, 0));
+        }
         for (int kk = 0; kk < k; ++kk) {
             auto step = [&](auto batch) {  // the nb frames of step st + kk as a simple strided batch
                 using BT = decltype(batch);
                 return BT{(decltype(batch.data))((char*)batch.data + batch.outerStride * kk), batch.pitch, batch.frameStride};
             };
             const bool resetStep = bt.st + kk == 0;  // id % R == 0
-            if (resetStep && (rc = launch_sp_reset(c, nb, slots, spS))) return rc;
             const ImgBatch<const uint8_t> sl = step(bl);
             const ImgBatch<int16_t> svm = step(vB);
             const ImgBatch<const int16_t> sv{svm.data, svm.pitch, svm.frameStride};
             const ImgBatch<uint16_t> so = step(lB);
+            if (split) {
+                const int its = resetStep ? o->sp_initial_iterations : o->sp_iterations;
+                for (int g = 0; g < G; ++g) {
+                    const int f0 = gOff[g], m = gOff[g + 1] - gOff[g];
+                    if (resetStep && (rc = launch_sp_reset(c, m, slots + f0, gStream(g)))) return rc;
+                    if ((rc = launch_sp_relax(c, m, slots + f0, its, sl.from(f0), sv.from(f0), true, so.from(f0), gStream(g), f0)))
+                        return rc;
+                }
+                continue;
+            }
+            if (resetStep && (rc = launch_sp_reset(c, nb, slots, spS))) return rc;
             // id == 1 also gets the initial iteration count (only chunk 0 at step 1 can be id 1)
             if (!resetStep && bt.idA + kk == 1) {
                 if ((rc = launch_sp_relax(c, 1, slots, o->sp_initial_iterations, sl, sv, true, so, spS))) return rc;
                 if (nb > 1 && (rc = launch_sp_relax(c, nb - 1, slots + 1, o->sp_iterations, sl.from(1), sv.from(1), true,
-                                                    so.from(1), spS)))
+                                                    so.from(1), spS, 1)))
                     return rc;
             } else {
                 const int its = resetStep ? o->sp_initial_iterations : o->sp_iterations;
                 if ((rc = launch_sp_relax(c, nb, slots, its, sl, sv, true, so, spS))) return rc;
+            }
+        }
+        if (split) {
+            for (int g = 1; g < G; ++g) {
+                CB_CHECK_CUDA(c, cudaEventRecord(q->evSpJoin[g - 1], gStream(g)));
+                CB_CHECK_CUDA(c, cudaStreamWaitEvent(spS, q->evSpJoin[g - 1], 0));
             }
         }
         if (!deferVote) {

@@ -145,7 +145,7 @@ int launch_naive_derivative(cartb200_ctx* c, int n, ImgBatch<const int16_t> disp
 int launch_classify(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, int channels, int channel, const int32_t* paramsDev, ImgBatch<uint8_t> planes, cudaStream_t s);
 int launch_sp_planeseg(cartb200_ctx* c, int n, ImgBatch<const int16_t> deriv, ImgBatch<const uint16_t> labels, int maxLabel, const int32_t* paramsDev, ImgBatch<uint8_t> unsm, ImgBatch<uint8_t> planes, cudaStream_t s);
 int launch_sp_reset(cartb200_ctx* c, int n, const int* slotsDev, cudaStream_t s);
-int launch_sp_relax(cartb200_ctx* c, int n, const int* slotsDev, int iterations, ImgBatch<const uint8_t> left, ImgBatch<const int16_t> deriv, bool hasDeriv, ImgBatch<uint16_t> out, cudaStream_t s);
+int launch_sp_relax(cartb200_ctx* c, int n, const int* slotsDev, int iterations, ImgBatch<const uint8_t> left, ImgBatch<const int16_t> deriv, bool hasDeriv, ImgBatch<uint16_t> out, cudaStream_t s, int scratchBase = 0);
 int launch_classify_temporal(cartb200_ctx* c, Img<const int16_t> deriv, int channels, int channel, PlaneRanges pr, const TemporalRefs& refs, Img<uint8_t> unsm, Img<uint8_t> smoothed, cudaStream_t s);
 int launch_sp_planeseg_temporal(cartb200_ctx* c, Img<const int16_t> deriv, Img<const uint16_t> labels, int maxLabel, PlaneRanges pr, const TemporalRefs& refs, Img<uint8_t> unsm, Img<uint8_t> planes, cudaStream_t s);
 int launch_label_statistics(cartb200_ctx* c, Img<const uint16_t> labels, Img<const float> xyz, int nLabels, uint32_t* count, uint32_t* invalid, cudaStream_t s);
