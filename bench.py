@@ -566,7 +566,7 @@ def main():
                 "aggregation_plus_wta": group,
                 "note": "compute-limited: every path recomputes the Hamming costs; per lane step (16 cells) the SASS holds 16 POPC "
                         "(XU pipe, 16 lanes/clk/SM: 128 clk) and 56 ALU-pipe instructions (64 lanes/clk/SM: 112 clk) - the "
-                        "POPC floor is 71 % of the HBM peak, the kernels run at 160 clk (DESIGN.md section 4)"}
+                        "POPC floor is 71 % of the HBM peak, the kernels run at 169 (horizontal) / 195 (vertical) clk (DESIGN.md section 4)"}
 
     cpu = None
     ref_gpu = None
