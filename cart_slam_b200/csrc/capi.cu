@@ -946,6 +946,8 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
             // the pipe-bound SGM kernels of the next batch fill the rest
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if (getenv("CARTB200_SP_PRIORITY") && atoi(getenv("CARTB200_SP_PRIORITY")) == 0) hi = lo;  // tuning aid: no priority
+            if (getenv("CARTB200_SP_PRIORITY") && atoi(getenv("CARTB200_SP_PRIORITY")) == 2) hi = (lo + hi) / 2;
             CB_CHECK_CUDA(c, cudaStreamCreateWithPriority(&q->spStream, cudaStreamNonBlocking, hi));
             for (auto& st : q->spStreamX) CB_CHECK_CUDA(c, cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
             CB_CHECK_CUDA(c, cudaEventCreateWithFlags(&q->evSpFork, cudaEventDisableTiming));
