@@ -1218,7 +1218,8 @@ int runSequence(cartb200_ctx* c, const cartb200_sequence_opts* o, int n, const u
         // independent chains: they are advanced as G groups on G streams, so that the partially filled last wave of one
         // group's relaxation launch (16 frames = 1920 tiles on 740 resident CTAs: 2.6 waves) is filled by the launches
         // of the other groups instead of idling.  CARTB200_SP_SPLIT = G (1 keeps one stream; measured: profiles/r02w_*).
-        static const int spGroups = std::max(1, std::min<int>(SeqScratch::kSpGroups, getenv("CARTB200_SP_SPLIT") ? atoi(getenv("CARTB200_SP_SPLIT")) : 2));
+        // (read per batch, not cached: the tests compare the group counts inside one process)
+        const int spGroups = std::max(1, std::min<int>(SeqScratch::kSpGroups, getenv("CARTB200_SP_SPLIT") ? atoi(getenv("CARTB200_SP_SPLIT")) : 2));
         // (the one step that gives frame id 1 its own iteration count keeps the single stream)
         const bool hasIdOne = bt.idA <= 1 && 1 < bt.idA + k && !(bt.st == 0 && bt.idA == 1);
         const int G = hasIdOne ? 1 : std::max(1, std::min(spGroups, nb / 2));

@@ -267,6 +267,37 @@ def test_sequence_superpixel_pipeline(gpu, provider, max_batch):
     assert np.array_equal(pd, planes)
 
 
+@pytest.mark.parametrize("provider", ["static", "histogram_peak"])
+def test_sequence_superpixel_chunk_groups(gpu, provider):
+    """Eight lock-stepped chunks (reset every 4 frames, 30 frames) in one slot group: the runner advances them as two
+    groups on two streams by default (CARTB200_SP_SPLIT groups; disjoint scratch ranges).  Planes and disparities equal
+    the oracle pipeline bit for bit, and 1 / 2 / 3 / 4 groups give the same bytes."""
+    W, H, D, n = 160, 64, 64, 30
+    seq, frames = _frames(W, H, D, n, tint=True)
+    cfgd = dict(D=D, radius=2, iters=1)
+    ref = rp.sp_sequence(frames, cfgd, provider=provider, update=5, reset=2, initial=5, steady=2, sp_reset=4, block=8)
+    L = np.stack([f[0] for f in frames])
+    R = np.stack([f[1] for f in frames])
+    cfg = cb.Config(W, H, max_batch=16, num_disparities=D, smoothing_radius=2, smoothing_iterations=1, sp_block_size=8)
+    opts = cb.SequenceOptions(pipeline=1, provider=0 if provider == "static" else 1, update_interval=5, reset_interval=2,
+                              sp_initial_iterations=5, sp_iterations=2, sp_reset_iterations=4)
+    got = {}
+    try:
+        with cb.Context(cfg) as ctx:
+            for g in ("2", "1", "3", "4"):
+                os.environ["CARTB200_SP_SPLIT"] = g
+                planes, disp = ctx.run_sequence_host(opts, L, R, want_disparity=True)
+                got[g] = (planes.copy(), disp.copy(), host(ctx.run_sequence_device(opts, dev(L), dev(R))))
+    finally:
+        os.environ.pop("CARTB200_SP_SPLIT", None)
+    planes, disp, pd = got["2"]
+    for i in range(n):
+        assert np.array_equal(disp[i], ref[i]["disparity"]), i
+        assert np.array_equal(planes[i], ref[i]["planes"]), i
+    for g, (p2, d2, pd2) in got.items():
+        assert np.array_equal(p2, planes) and np.array_equal(d2, disp) and np.array_equal(pd2, planes), f"{g} groups"
+
+
 def test_full_size_kitti_properties(gpu):
     """BASELINE.json full size (1242x375, D=128): size-independent properties instead of the slow oracle."""
     W, H, D = 1242, 375, 128

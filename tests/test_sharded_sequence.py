@@ -159,12 +159,14 @@ def test_phase2_needs_its_phase1(gpu):
 
 
 @pytest.mark.gpu
-def test_headline_shape_sequence_equals_per_stage_composition(gpu):
+@pytest.mark.parametrize("n,reset", [(134, 64), (70, 16)])
+def test_headline_shape_sequence_equals_per_stage_composition(gpu, n, reset):
     """BENCH's shape: 1242x375, 128 disparities, batch 64, reset 64, 24 / 8 iterations, histogram_peak; 134 frames =
-    chunks [1..63], [64..127], [128..134] advanced in lock step.  Every frame's planes equal the composition of the
+    chunks [1..63], [64..127], [128..134] advanced in lock step (and 70 frames with reset 16: five chunks, which the
+    runner advances as two groups on two streams).  Every frame's planes equal the composition of the
     per-stage entry points (each oracle-checked in test_gpu_parity.py) driven by the reference's schedule; three
     sampled frames are also checked against the oracle itself."""
-    W, H, D, n, reset = 1242, 375, 128, 134, 64
+    W, H, D = 1242, 375, 128
     seq = SyntheticSequence(W, H, D, n_frames=8, tint=True)
     base = [seq.frame(1 + i)[:2] for i in range(8)]
     rng = np.random.default_rng(5)
@@ -182,7 +184,7 @@ def test_headline_shape_sequence_equals_per_stage_composition(gpu):
     with cb.Context(cfg) as ctx:
         planes, disp = ctx.run_sequence_device(opts, dL, dR, want_disparity=True)
         planes, disp = host(planes), host(disp)
-    sample = {1: None, 64: None, 130: None}
+    sample = {1: None, reset: None, n - 4: None}
     cfg1 = cb.Config(W, H, max_batch=1, num_disparities=D, smoothing_radius=2, smoothing_iterations=1, sp_block_size=12)
     hists = np.zeros((n, 256), np.int32)
     keep = []
