@@ -46,7 +46,9 @@ UNIT = "frames/s"
 WORKLOADS = {
     "kitti": dict(W=1242, H=375, D=128, paths=4, block=12, frames=1000, batch=64, pipeline=1, provider=1),
     "zed": dict(W=1280, H=720, D=256, paths=4, block=16, frames=200, batch=16, pipeline=1, provider=0),
-    "4k": dict(W=3840, H=2160, D=256, paths=8, block=48, frames=20, batch=4, pipeline=0, provider=1),
+    # batch 8: 139 GB of scratch (17 GB of path volumes per frame) - a 4-frame batch leaves the vertical and diagonal path
+    # kernels short of warps (aggregation 0.43 of the HBM peak instead of 0.46, profiles/r02x_bench_4k_batch_sweep.json)
+    "4k": dict(W=3840, H=2160, D=256, paths=8, block=48, frames=20, batch=8, pipeline=0, provider=1),
 }
 
 
@@ -262,7 +264,7 @@ def other_configs():
     sequence (the full-length lines are under profiles/): keeps every configuration of BASELINE.json in the driver's record."""
     runs = {
         "zed_config2": ["--workload", "zed", "--frames", "64"],
-        "4k_8path_config3": ["--workload", "4k", "--frames", "8"],
+        "4k_8path_config3": ["--workload", "4k", "--frames", "16"],
         "kitti_naive_pipeline": ["--workload", "kitti", "--pipeline", "0", "--frames", "256"],
     }
     out = {}
