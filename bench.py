@@ -45,7 +45,7 @@ UNIT = "frames/s"
 # BASELINE.json configs: [1] is the headline (default); [2] and [3] are recorded with --workload zed / 4k
 WORKLOADS = {
     "kitti": dict(W=1242, H=375, D=128, paths=4, block=12, frames=1000, batch=64, pipeline=1, provider=1),
-    "zed": dict(W=1280, H=720, D=256, paths=4, block=16, frames=200, batch=16, pipeline=1, provider=0),
+    "zed": dict(W=1280, H=720, D=256, paths=4, block=16, frames=200, batch=32, pipeline=1, provider=0),
     # batch 8: 139 GB of scratch (17 GB of path volumes per frame) - a 4-frame batch leaves the vertical and diagonal path
     # kernels short of warps (aggregation 0.43 of the HBM peak instead of 0.46, profiles/r02x_bench_4k_batch_sweep.json)
     "4k": dict(W=3840, H=2160, D=256, paths=8, block=48, frames=20, batch=8, pipeline=0, provider=1),
