@@ -2,7 +2,9 @@
 // points and the whole-sequence runner that reproduces the reference's per-sequence state.
 #include <algorithm>
 #include <cstring>
+#include <climits>
 #include <new>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -866,20 +868,26 @@ struct HistState {
     int32_t params[6] = {0, 0, 0, 0, 0, 0};  // hC, vC, hS, hE, vS, vE
 };
 
-// naive module bookkeeping for frame `id` whose own histogram is `h`; writes the ranges to use
-void naiveUpdate(HistState& st, const cartb200_sequence_opts& o, int id, const int32_t* h, int32_t* outParams) {
+// naive module bookkeeping for frame `id` whose own histogram is `h`; writes the ranges to use.  `peak(snapshot)` is what
+// happens at an update frame: by default the provider's update on the running parameters
+template <class Peak>
+void naiveUpdateT(HistState& st, const cartb200_sequence_opts& o, int id, const int32_t* h, int32_t* outParams, Peak&& peak) {
     for (int i = 0; i < 256; ++i) st.running[i] += h[i];  // mergeHistogram (planeseg.cu:144-158)
     if (o.provider == 1 && id % o.update_interval == 1) {
         int32_t snap[256];
         for (int i = 0; i < 256; ++i) snap[i] = (int32_t)st.running[i];
         if (id % (o.update_interval * o.reset_interval) == 1) std::fill(st.running.begin(), st.running.end(), 0);
-        cb::histogram_peak_update(snap, st.params);
+        peak(snap);
     }
     std::memcpy(outParams, st.params + 2, 4 * sizeof(int32_t));
 }
+void naiveUpdate(HistState& st, const cartb200_sequence_opts& o, int id, const int32_t* h, int32_t* outParams) {
+    naiveUpdateT(st, o, id, h, outParams, [&](const int32_t* snap) { cb::histogram_peak_update(snap, st.params); });
+}
 
 // SP module bookkeeping; h = vertical channel of the frame's derivative histogram
-void spUpdate(HistState& st, const cartb200_sequence_opts& o, int id, const int32_t* hv, int32_t* outParams) {
+template <class Peak>
+void spUpdateT(HistState& st, const cartb200_sequence_opts& o, int id, const int32_t* hv, int32_t* outParams, Peak&& peak) {
     int32_t hist[256];
     if (!st.created) {
         st.created = true;  // zeros; the first frame is NOT added (sp_planeseg.cu:364-366)
@@ -891,8 +899,11 @@ void spUpdate(HistState& st, const cartb200_sequence_opts& o, int id, const int3
         }
     }
     if (id % (o.update_interval * o.reset_interval) == 1) std::fill(st.running.begin(), st.running.end(), 0);
-    if (o.provider == 1 && id % o.update_interval == 1) cb::histogram_peak_update(hist, st.params);
+    if (o.provider == 1 && id % o.update_interval == 1) peak(hist);
     std::memcpy(outParams, st.params + 2, 4 * sizeof(int32_t));
+}
+void spUpdate(HistState& st, const cartb200_sequence_opts& o, int id, const int32_t* hv, int32_t* outParams) {
+    spUpdateT(st, o, id, hv, outParams, [&](const int32_t* hist) { cb::histogram_peak_update(hist, st.params); });
 }
 
 // phase 0: the whole pipeline.  phase 1: everything up to the per-frame histograms (copied to histOut, HOST, n x 256, the
@@ -1357,11 +1368,52 @@ int cartb200_sequence_parameters(const cartb200_sequence_opts* o, int n, const i
         hs.params[4] = o->static_params[2];
         hs.params[5] = o->static_params[3];
     }
+    // The running-histogram bookkeeping is sequential and cheap (0.14 us per frame); the peak detection at the update
+    // frames (24 us each: two std::sort calls) is a pure function of the snapshot, which writes a subset of the six
+    // parameters and reads none.  For long sequences - one 10,000-frame sequence sharded over N GPUs runs this table on
+    // every rank between its two phases - the snapshots are taken first, the peak updates run on a few threads, and the
+    // results are applied in frame order.  Same numbers as the frame-by-frame loop (tests/test_sharded_sequence.py).
+    const bool threaded = o->provider == 1 && n >= 2048;
+    if (!threaded) {
+        for (int i = 0; i < n; ++i) {
+            if (o->pipeline == 0)
+                naiveUpdate(hs, *o, o->start_id + i, hist + 256 * (size_t)i, params + 4 * (size_t)i);
+            else
+                spUpdate(hs, *o, o->start_id + i, hist + 256 * (size_t)i, params + 4 * (size_t)i);
+        }
+        return CARTB200_OK;
+    }
+    std::vector<int32_t> snaps;           // [updates][256]
+    std::vector<int> updateOf((size_t)n, -1);
     for (int i = 0; i < n; ++i) {
+        auto take = [&](const int32_t* snap) {
+            updateOf[(size_t)i] = (int)(snaps.size() / 256);
+            snaps.insert(snaps.end(), snap, snap + 256);
+        };
         if (o->pipeline == 0)
-            naiveUpdate(hs, *o, o->start_id + i, hist + 256 * (size_t)i, params + 4 * (size_t)i);
+            naiveUpdateT(hs, *o, o->start_id + i, hist + 256 * (size_t)i, params + 4 * (size_t)i, take);
         else
-            spUpdate(hs, *o, o->start_id + i, hist + 256 * (size_t)i, params + 4 * (size_t)i);
+            spUpdateT(hs, *o, o->start_id + i, hist + 256 * (size_t)i, params + 4 * (size_t)i, take);
+    }
+    const int nUpd = (int)(snaps.size() / 256);
+    constexpr int32_t kUntouched = INT32_MIN;  // no parameter can take this value (bins are 0..255)
+    std::vector<int32_t> cand((size_t)nUpd * 6, kUntouched);
+    const int nThreads = std::max(1, std::min<int>({8, (int)std::thread::hardware_concurrency(), nUpd / 8}));
+    auto work = [&](int t) {
+        for (int u = t; u < nUpd; u += nThreads) cb::histogram_peak_update(snaps.data() + 256 * (size_t)u, cand.data() + 6 * (size_t)u);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nThreads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    int32_t cur[6];
+    std::memcpy(cur, hs.params, sizeof(cur));  // still the start values: the snapshot pass never updated them
+    for (int i = 0; i < n; ++i) {  // replay in frame order
+        const int u = updateOf[(size_t)i];
+        if (u >= 0)
+            for (int f = 0; f < 6; ++f)
+                if (cand[6 * (size_t)u + f] != kUntouched) cur[f] = cand[6 * (size_t)u + f];
+        std::memcpy(params + 4 * (size_t)i, cur + 2, 4 * sizeof(int32_t));
     }
     return CARTB200_OK;
 }

@@ -68,6 +68,32 @@ def test_sequence_parameters_match_the_reference_bookkeeping(pipeline, provider,
         assert len({tuple(r) for r in got.tolist()}) > 1, "the peak provider never changed the ranges on the test data"
 
 
+@pytest.mark.parametrize("pipeline", [0, 1])
+def test_sequence_parameters_long_table_threaded_path(pipeline):
+    """From 2048 frames on, the table takes the snapshots first, runs the peak updates on a few threads and applies them in
+    frame order (the 10,000-frame sharded run computes it on every rank): same numbers as the frame-by-frame oracle,
+    failing updates (flat histograms, which keep the previous ranges) included."""
+    rng = np.random.default_rng(99 + pipeline)
+    n = 2600
+    x = np.arange(256)
+    hists = np.empty((n, 256), np.int32)
+    for i in range(n):
+        if rng.random() < 0.15:
+            hists[i] = rng.integers(0, 2, 256)  # (almost) nothing: whole update windows of these make the update fail
+        else:
+            a, b = 128 + rng.integers(-3, 4), 140 + rng.integers(0, 25)
+            h = 4000 * np.exp(-0.5 * ((x - a) / 2.0) ** 2) + 900 * np.exp(-0.5 * ((x - b) / 3.0) ** 2)
+            hists[i] = (h + rng.integers(0, 30, 256)).astype(np.int32)
+    hists[300:420] = 0  # several consecutive update windows without any data
+    for start_id in (1, 64):
+        opts = cb.SequenceOptions(pipeline=pipeline, provider=1, static_params=(1, 30, -3, 1), update_interval=7,
+                                  reset_interval=4, start_id=start_id)
+        got = cb.sequence_parameters(opts, hists)
+        want = _schedule_oracle(pipeline, 1, (1, 30, -3, 1), 7, 4, start_id, hists)
+        assert np.array_equal(got, want), start_id
+        assert np.array_equal(got[:2000], cb.sequence_parameters(opts, hists[:2000]))  # the sequential path on the prefix
+
+
 # ---- GPU -----------------------------------------------------------------------------------------------------------
 torch = pytest.importorskip("torch")
 
