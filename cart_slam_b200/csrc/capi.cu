@@ -1,6 +1,7 @@
 // C ABI of libcartb200 (include/cartb200.h): context management, argument validation, stage entry
 // points and the whole-sequence runner that reproduces the reference's per-sequence state.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <climits>
 #include <new>
@@ -1399,12 +1400,16 @@ int cartb200_sequence_parameters(const cartb200_sequence_opts* o, int n, const i
     constexpr int32_t kUntouched = INT32_MIN;  // no parameter can take this value (bins are 0..255)
     std::vector<int32_t> cand((size_t)nUpd * 6, kUntouched);
     const int nThreads = std::max(1, std::min<int>({8, (int)std::thread::hardware_concurrency(), nUpd / 8}));
-    auto work = [&](int t) {
-        for (int u = t; u < nUpd; u += nThreads) cb::histogram_peak_update(snaps.data() + 256 * (size_t)u, cand.data() + 6 * (size_t)u);
+    std::atomic<int> next{0};
+    auto work = [&]() {  // updates are handed out one at a time: any number of workers, this thread included, finishes the list
+        for (int u; (u = next.fetch_add(1)) < nUpd;) cb::histogram_peak_update(snaps.data() + 256 * (size_t)u, cand.data() + 6 * (size_t)u);
     };
     std::vector<std::thread> pool;
-    for (int t = 1; t < nThreads; ++t) pool.emplace_back(work, t);
-    work(0);
+    try {
+        for (int t = 1; t < nThreads; ++t) pool.emplace_back(work);
+    } catch (...) {  // no more threads to be had: no exception may cross the C ABI, the calling thread does the rest
+    }
+    work();
     for (auto& th : pool) th.join();
     int32_t cur[6];
     std::memcpy(cur, hs.params, sizeof(cur));  // still the start values: the snapshot pass never updated them
