@@ -68,3 +68,31 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["metric"] == bench.METRIC and d["higher_is_better"] is True
+
+
+def test_committed_bench_line_carries_the_contract_keys():
+    """The newest committed default bench line (profiles/r*_bench_default_n1.json): base-contract keys, the roofline of
+    the aggregation kernels with live timing and matching ncu traffic, the aggregation + WTA group of SURVEY 8(d) with
+    its algorithmic bytes 2 P W H D + (8 P + 27) W H per frame, the CPU baseline and the end-to-end object."""
+    import glob
+    lines = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_bench_default_n1.json")))
+    d = json.loads(open(lines[-1]).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["vs_baseline"] is None
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["e2e"]["h2d_bytes_per_step"] == 2 * 1000 * 375 * 1242 * 3 and d["e2e"]["d2h_bytes_per_step"] == 1000 * 375 * 1242
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    W, H, D, B, P = 1242, 375, 128, 64, 4
+    assert r["algorithmic_bytes_per_launch"] == B * (2 * 4 * W * H + W * H * D)
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["launch_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    if r["traffic"] is not None:
+        assert abs(r["traffic"] / r["algorithmic_bytes_per_launch"] - 1.0) < 0.03
+    g = r["aggregation_plus_wta"]
+    assert g["algorithmic_bytes"] == B * (2 * P * W * H * D + (8 * P + 27) * W * H)
+    assert abs(g["frac"] - g["algorithmic_bytes"] / (g["ms"] * 1e-3) / 1e9 / r["peak"]) < 1e-9
+    assert abs(g["ms"] - (g["aggregation_ms"] + g["wta_post_interp_ms"])) < 1e-9
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["sample"]
