@@ -25,6 +25,7 @@ def _load():
     lib.cartb200_host_run_config.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cartb200_host_decode_png.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.cartb200_host_inflate.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
     lib.cartb200_host_run_source.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cartb200_host_run_config_ex.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -67,6 +68,15 @@ def decode_png(path):
     out = np.empty((h.value, w.value, 3), np.uint8)
     if _lib.cartb200_host_decode_png(str(path).encode(), out.ctypes.data, out.nbytes, C.byref(w), C.byref(h)) != 0:
         raise HostError(_lib.cartb200_host_last_error().decode())
+    return out
+
+
+def inflate(stream: bytes, size: int, repeat: int = 1):
+    """The PNG reader's own zlib-stream decoder: `stream` must decode to exactly `size` bytes (returns them as a uint8
+    array) - raises HostError on a malformed / truncated / mis-sized stream or an Adler-32 mismatch."""
+    out = np.empty(size, np.uint8)
+    if _lib.cartb200_host_inflate(stream, len(stream), out.ctypes.data, size, repeat) != 0:
+        raise HostError("inflate failed")
     return out
 
 

@@ -9,6 +9,7 @@
 
 #include "cart/modules.hpp"
 #include "cart/sources.hpp"
+#include "cart/inflate.hpp"
 
 namespace {
 std::string g_error;
@@ -108,6 +109,23 @@ int cartb200_host_decode_png(const char* path, uint8_t* out, size_t out_capacity
     } catch (const std::exception& e) {
         g_error.clear();
         describe(e, g_error);
+        return -1;
+    }
+}
+
+// The PNG reader's zlib-stream decoder on a caller's buffers (tests, tools/inflate_bench.py).  Returns 0 when `in` decodes
+// to exactly out_size bytes with a matching Adler-32, -1 otherwise.  repeat > 1 decodes that many times (timing).
+int cartb200_host_inflate(const uint8_t* in, size_t in_size, uint8_t* out, size_t out_size, int repeat) {
+    if (!in || (!out && out_size)) return -1;
+    try {
+        std::vector<uint8_t> src(in_size + cart::png::kInflatePad, 0), dst(out_size + cart::png::kInflatePad);
+        std::memcpy(src.data(), in, in_size);
+        bool ok = true;
+        for (int r = 0; r < (repeat > 1 ? repeat : 1) && ok; ++r) ok = cart::png::inflateZlib(src.data(), in_size, dst.data(), out_size);
+        if (!ok) return -1;
+        if (out_size) std::memcpy(out, dst.data(), out_size);
+        return 0;
+    } catch (const std::exception&) {
         return -1;
     }
 }

@@ -1,5 +1,6 @@
 // KITTI odometry data source + PNG reader (see cart/sources.hpp for the reference files this follows).
 #include "cart/sources.hpp"
+#include "cart/inflate.hpp"
 
 #include <cuda_runtime.h>
 
@@ -82,10 +83,19 @@ void readPngBgr(const std::string& path, std::vector<uint8_t>& bgr, int& width, 
     }
     if (colorType == 3 && palette.size() < 3) throw std::runtime_error(path + ": palette image without PLTE");
     const size_t stride = (size_t)width * ch;
-    std::vector<uint8_t> raw((stride + 1) * (size_t)height);
-    uLongf rawLen = (uLongf)raw.size();
-    if (uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size()) != Z_OK || rawLen != raw.size())
+    const size_t rawSize = (stride + 1) * (size_t)height;
+    std::vector<uint8_t> raw(rawSize + png::kInflatePad);
+    // own zlib-stream decoder (cart/inflate.hpp: whole-buffer, known output size); CARTB200_PNG_ZLIB=1 uses zlib's
+    const size_t idatSize = idat.size();
+    idat.resize(idatSize + png::kInflatePad, 0);
+    static const bool useZlib = getenv("CARTB200_PNG_ZLIB") && atoi(getenv("CARTB200_PNG_ZLIB")) != 0;
+    if (useZlib) {
+        uLongf rawLen = (uLongf)rawSize;
+        if (uncompress(raw.data(), &rawLen, idat.data(), (uLong)idatSize) != Z_OK || rawLen != rawSize)
+            throw std::runtime_error(path + ": PNG inflate failed");
+    } else if (!png::inflateZlib(idat.data(), idatSize, raw.data(), rawSize)) {
         throw std::runtime_error(path + ": PNG inflate failed");
+    }
     // undo the scanline filters in place, one specialised loop per filter type (the per-byte dispatch of a generic
     // loop costs more than the inflate)
     bgr.resize((size_t)width * height * 3);

@@ -25,6 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=96)
     ap.add_argument("--distinct", type=int, default=8)
+    ap.add_argument("--quick", action="store_true", help="decoder timing + disk -> planes with the default decode threads only")
     args = ap.parse_args()
     W, H, D = 1242, 375, 128
     root = "/tmp/cartb200_disk_bench"
@@ -59,14 +60,15 @@ def main():
     Lm = np.stack([frames[i % args.distinct][0] for i in range(args.frames)])
     Rm = np.stack([frames[i % args.distinct][1] for i in range(args.frames)])
     host.run_config(modules, Lm[:8], Rm[:8], sequential=False)
-    for name, sq in (("memory_to_planes_fps_in_flight_12", False), ("memory_to_planes_fps_sequential", True)):
+    for name, sq in (("memory_to_planes_fps_in_flight_12", False),) if args.quick else (("memory_to_planes_fps_in_flight_12", False), ("memory_to_planes_fps_sequential", True)):
         t0 = time.perf_counter()
         host.run_config(modules, Lm, Rm, sequential=sq)
         out[name] = args.frames / (time.perf_counter() - t0)
     t0 = time.perf_counter()
     host.run_config(modules, Lm[:1], Rm[:1], sequential=True)
     out["setup_plus_one_frame_s"] = time.perf_counter() - t0
-    for threads in (1, 4, None):
+    out["png_inflate"] = "zlib" if os.environ.get("CARTB200_PNG_ZLIB", "0") not in ("", "0") else "own (cart/inflate.hpp)"
+    for threads in ((None,) if args.quick else (1, 4, None)):
         if threads:
             os.environ["CARTB200_KITTI_DECODE_THREADS"] = str(threads)
         else:
