@@ -25,6 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=96)
     ap.add_argument("--distinct", type=int, default=8)
+    ap.add_argument("--repeat", type=int, default=1, help="repetitions of every disk -> planes measurement (all values are reported)")
     ap.add_argument("--quick", action="store_true", help="decoder timing + disk -> planes with the default decode threads only")
     args = ap.parse_args()
     W, H, D = 1242, 375, 128
@@ -74,11 +75,14 @@ def main():
         else:
             os.environ.pop("CARTB200_KITTI_DECODE_THREADS", None)
         host.run_source(source, modules, 8)  # warm-up
-        t0 = time.perf_counter()
-        res = host.run_source(source, modules, args.frames)
-        dt = time.perf_counter() - t0
-        n = res["planes"].shape[0] if isinstance(res, dict) and "planes" in res else args.frames
-        out[f"disk_to_planes_fps_decode_threads_{threads or 'default'}"] = n / dt
+        vals = []
+        for _ in range(max(1, args.repeat)):
+            t0 = time.perf_counter()
+            res = host.run_source(source, modules, args.frames)
+            dt = time.perf_counter() - t0
+            n = res["planes"].shape[0] if isinstance(res, dict) and "planes" in res else args.frames
+            vals.append(n / dt)
+        out[f"disk_to_planes_fps_decode_threads_{threads or 'default'}"] = vals[0] if args.repeat <= 1 else sorted(vals)
     print(json.dumps(out, indent=1))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "disk_bench.json"), "w"), indent=1)
