@@ -39,14 +39,18 @@ void readPngBgr(const std::string& path, std::vector<uint8_t>& bgr, int& width, 
     std::ifstream f(path, std::ios::binary | std::ios::ate);
     if (!f.is_open()) throw std::runtime_error("Failed to open image " + path + ": " + strerror(errno));
     const std::streamsize fileSize = f.tellg();
-    std::vector<uint8_t> file(fileSize > 0 ? (size_t)fileSize : 0);
+    // the three working buffers (file, compressed stream, filtered scanlines) are kept per decode thread: a fresh 1.4 MB
+    // vector per image costs its zero fill and its page faults again for every frame
+    static thread_local std::vector<uint8_t> file, idat, raw;
+    file.resize(fileSize > 0 ? (size_t)fileSize : 0);
     f.seekg(0);
     if (!file.empty() && !f.read(reinterpret_cast<char*>(file.data()), fileSize)) throw std::runtime_error("Failed to read image " + path);
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     if (file.size() < 8 + 25 || std::memcmp(file.data(), sig, 8) != 0) throw std::runtime_error(path + ": not a PNG file");
     int bitDepth = 0, colorType = 0, interlace = 0;
     width = height = 0;
-    std::vector<uint8_t> idat, palette;
+    std::vector<uint8_t> palette;
+    idat.clear();
     size_t pos = 8;
     bool end = false;
     while (!end && pos + 12 <= file.size()) {
@@ -84,7 +88,7 @@ void readPngBgr(const std::string& path, std::vector<uint8_t>& bgr, int& width, 
     if (colorType == 3 && palette.size() < 3) throw std::runtime_error(path + ": palette image without PLTE");
     const size_t stride = (size_t)width * ch;
     const size_t rawSize = (stride + 1) * (size_t)height;
-    std::vector<uint8_t> raw(rawSize + png::kInflatePad);
+    if (raw.size() < rawSize + png::kInflatePad) raw.resize(rawSize + png::kInflatePad);
     // own zlib-stream decoder (cart/inflate.hpp: whole-buffer, known output size); CARTB200_PNG_ZLIB=1 uses zlib's
     const size_t idatSize = idat.size();
     idat.resize(idatSize + png::kInflatePad, 0);
